@@ -1,0 +1,160 @@
+/*
+ * bhr.h -- C ABI of libbhr.so, the B200 (sm_100a) implementation of hwuu/black-hole-renderer's
+ * per-pixel null-geodesic render path.
+ *
+ * The reference has no FFI of its own: its device code is reached only through the Python class
+ * `TaichiRenderer` (render.py:2189-4028), whose methods launch Taichi kernels.  Each entry point
+ * below replaces one of those methods / kernels and cites it.  The Python class
+ * black_hole_renderer_b200.Renderer (same constructor and method surface as TaichiRenderer)
+ * binds these symbols with ctypes; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions: every function returns 0 on success and a non-zero bhr_status otherwise (the
+ * message is available from bhr_last_error); no exceptions cross the ABI; host buffers are owned
+ * by the caller, device buffers by the context; one CUDA stream per context (bhr_set_stream lets
+ * the host supply it); a context is not thread-safe; one context per GPU.  Images are row-major
+ * (H, W, 3) -- the reference's (W, H) fields transposed as render() does on return
+ * (render.py:3923).  All device arithmetic is float32 (the lens flare uses float64 like the
+ * reference's numpy implementation).
+ */
+#ifndef BHR_H_
+#define BHR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bhr_ctx bhr_ctx;
+
+typedef enum {
+    BHR_OK = 0,
+    BHR_ERR_INVALID = 1,   /* bad argument / size mismatch (the reference raises AssertionError) */
+    BHR_ERR_CUDA = 2,      /* CUDA runtime failure                                                */
+    BHR_ERR_STATE = 3,     /* call order violated (e.g. generate_background before init)          */
+    BHR_ERR_NOMEM = 4
+} bhr_status;
+
+/* TaichiRenderer.__init__ arguments, render.py:2199-2208 */
+typedef struct {
+    int32_t width, height;
+    float step_size;            /* h_base                                   */
+    float r_max;
+    float r_disk_inner, r_disk_outer;
+    float disk_tilt_deg;
+    int32_t lens_flare;         /* mutable later through bhr_set_lens_flare */
+    int32_t anti_alias;         /* 0 = "disabled", 1 = "lod_radius"         */
+    float aa_strength;
+    float disk_rotation_speed;  /* t_offset = frame * speed (render.py:3897) */
+    int32_t device;             /* CUDA device ordinal                      */
+} bhr_config;
+
+/* What TaichiRenderer.render uploads per frame (render.py:3880-3892): build_camera's float64
+ * results cast to f32, the pixel pitch and r_escape = max(r_max, 2|cam|). */
+typedef struct {
+    float pos[3], right[3], up[3], forward[3];
+    float pixel_w, pixel_h;
+    float r_escape;
+    float t_offset;
+} bhr_camera;
+
+/* bhr_render flags */
+#define BHR_SKIP_DIFFERENTIALS 1u   /* render(skip_differentials=True), render.py:3900 */
+#define BHR_SKIP_BLOOM 2u           /* render(skip_bloom=True), render.py:3911         */
+#define BHR_WANT_AUX 4u             /* also fill the class / step-count buffers        */
+
+/* device buffers that can be inspected / exchanged (bhr_buffer, bhr_download) */
+typedef enum {
+    BHR_BUF_BG = 0,        /* image_field: planar 3 x (H, W) f32                         */
+    BHR_BUF_DISK = 1,      /* disk_layer_field before bloom: planar 3 x (H, W) f32       */
+    BHR_BUF_HBLUR = 2,     /* bright_field after the horizontal pass: planar 3 x (H, W)  */
+    BHR_BUF_FINAL = 3,     /* (H, W, 3) f32, render()'s return value                     */
+    BHR_BUF_FINAL_U8 = 4,  /* (H, W, 3) u8 = trunc(clip(final) * 255), render.py:4463    */
+    BHR_BUF_CLASS = 5,     /* (H, W) u8: bits 0-1 termination (0 exhausted, 1 horizon, 2 escaped), bit 2 = disk hit */
+    BHR_BUF_STEPS = 6,     /* (H, W) i32 RK4 evaluations per ray                         */
+    BHR_BUF_DISK_TEX = 7,  /* disk_texture_field: (n_r, n_phi, 4) f32                    */
+    BHR_BUF_DISK_MIPS = 8, /* compact pyramid, level l = (n_r>>l, n_phi>>l, 4) f32       */
+    BHR_BUF_COMP = 9,      /* _comp_field: (13, n_r, n_phi) f32                          */
+    BHR_BUF_BLUR = 10      /* blur_field (after the vertical pass): planar 3 x (H, W)    */
+} bhr_buffer_id;
+
+/* ---- lifecycle (TaichiRenderer.__init__, render.py:2199-2290) ---- */
+int bhr_create(const bhr_config* cfg, bhr_ctx** out);
+void bhr_destroy(bhr_ctx* ctx);
+const char* bhr_last_error(const bhr_ctx* ctx); /* ctx may be NULL: error of a failed bhr_create */
+int bhr_set_stream(bhr_ctx* ctx, void* cuda_stream); /* NULL = the context's own stream */
+int bhr_synchronize(bhr_ctx* ctx);
+int bhr_set_lens_flare(bhr_ctx* ctx, int enabled);  /* renderer.lens_flare attribute */
+int bhr_version(void);
+
+/* texture_field.from_numpy (render.py:2232-2233): skybox (h, w, 3) f32 host */
+int bhr_upload_skybox(bhr_ctx* ctx, const float* rgb, int h, int w);
+/* __init__/update_disk_texture (render.py:2235-2251, 2292-2312): (n_r, n_phi, 4) f32 host;
+ * rebuilds the 5-level mip pyramid in generate_disk_mipmaps' summation order. The first call
+ * fixes (n_r, n_phi); later calls must match (the reference asserts). */
+int bhr_upload_disk_texture(bhr_ctx* ctx, const float* rgba, int n_r, int n_phi);
+
+/* ---- hot path (TaichiRenderer.render, render.py:3865-3923) ---- */
+/* Ray march + bloom + composite [+ flare]; if out_f32 / out_u8 are non-NULL the (H, W, 3)
+ * result is copied to those HOST buffers (the call then synchronises). */
+int bhr_render(bhr_ctx* ctx, const bhr_camera* cam, uint32_t flags, float* out_f32, uint8_t* out_u8);
+
+/* Row-tile variants used when one frame is split over several GPUs.  Stage 1 ray
+ * marches rows [row0, row1) and runs the horizontal bloom pass on them; the caller then exchanges
+ * the radius-row halos of BHR_BUF_HBLUR between neighbours (NCCL) and, for the flare, all-reduces
+ * the three brightness sums; stage 2 runs the vertical pass + composite (+ flare) on the rows. */
+int bhr_render_rows_stage1(bhr_ctx* ctx, const bhr_camera* cam, uint32_t flags, int row0, int row1);
+int bhr_render_rows_stage2(bhr_ctx* ctx, uint32_t flags, int row0, int row1,
+                           const double* flare_sums /* NULL or {sum B, sum x*B, sum y*B} */);
+int bhr_flare_sums(bhr_ctx* ctx, int row0, int row1, double out[3]);
+int bhr_bloom_radius(const bhr_ctx* ctx);
+
+/* ---- device buffers ---- */
+int bhr_buffer(bhr_ctx* ctx, int id, void** dev_ptr, size_t* bytes);
+int bhr_download(bhr_ctx* ctx, int id, void* host, size_t bytes);
+/* total RK4 evaluations of the last ray march (sum over pixels); feeds the flop count */
+int bhr_last_total_steps(bhr_ctx* ctx, uint64_t* out);
+/* device time (ms, CUDA events) of the stages of the last bhr_render: {ray march, bloom H,
+ * bloom V + composite, flare, total}; valid after bhr_synchronize */
+int bhr_last_stage_ms(bhr_ctx* ctx, float out[5]);
+
+/* ---- disk-texture pipeline (render.py:3491-3767) ---- */
+/* init_background_layer (render.py:3491-3547): allocates comp (13, n_r, n_phi), uploads edge /
+ * omega rows, seeds the initial stats.  az_freq / az_shear are the two numbers the reference
+ * draws from default_rng(seed) (render.py:3510-3511). */
+int bhr_init_background(bhr_ctx* ctx, int n_r, int n_phi, int az_freq, float az_shear,
+                        const float* edge, const float* omega_rows);
+/* generate_background (render.py:3549-3562) -> _generate_background_kernel (3332-3451) */
+int bhr_generate_background(bhr_ctx* ctx, float t);
+
+/* One entity of the lifecycle system as the accumulate kernel consumes it
+ * (accumulate_entity_layer, render.py:3564-3653).  kind 0 = filament (Gaussian blob sheared by
+ * differential rotation), 1 = hotspot, 2 = rt_spike (analytic profiles of
+ * _spawn_single_hotspot / _spawn_single_rt_spike, render.py:1725-1866, rolled per row). */
+typedef struct {
+    int32_t kind;
+    int32_t row_begin, row_end;   /* affected rows [row_begin, row_end)        */
+    double age;                   /* now - birth_time                          */
+    double scale;                 /* filament: birth_alpha*cool_factor*s0/sigma_t ; others: fade alpha */
+    double p[8];                  /* kind-specific parameters, see texture.cu  */
+} bhr_entity;
+int bhr_accumulate_entities(bhr_ctx* ctx, const bhr_entity* entities, int n);
+/* recompute_interactive_stats (render.py:3655-3712) stays on the host at first: read comp back,
+ * then upload the two scalars + per-row (max, p70). */
+int bhr_set_stats(bhr_ctx* ctx, float density_p98, float struct_scale, const float* row_stats /* (n_r, 2) */);
+int bhr_upload_comp(bhr_ctx* ctx, const float* comp /* (13, n_r, n_phi) */);
+/* compose_interactive_texture (render.py:3714-3767): compose kernel + mip kernels */
+int bhr_compose_texture(bhr_ctx* ctx, float t_offset, int enable_rt, float color_temp);
+/* eval_noise (render.py:3769-3790): mode 0 simplex, 1 fbm; coords (n, 3) host -> out (n) host */
+int bhr_eval_noise(bhr_ctx* ctx, const float* coords, int n, int mode, int octaves,
+                   float persistence, float lacunarity, float* out);
+
+/* ---- measurement helpers ---- */
+/* FP32 FMA throughput microbenchmark (TFLOP/s): mode 0 scalar FFMA, 1 packed FFMA2 */
+int bhr_measure_fp32_peak(int device, int mode, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BHR_H_ */
