@@ -1,0 +1,299 @@
+// api.cu -- context lifecycle and the C-ABI entry points of libbhr.so (see include/bhr.h).
+#include <math.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+
+char g_bhr_create_error[512] = "";
+extern int bhr_raymarch_mode_override;
+
+#define CREATE_CHECK(call)                                                                              \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess) {                                                                        \
+            snprintf(g_bhr_create_error, sizeof(g_bhr_create_error), "%s: %s", #call, cudaGetErrorString(e_)); \
+            bhr_destroy(ctx);                                                                           \
+            return BHR_ERR_CUDA;                                                                        \
+        }                                                                                               \
+    } while (0)
+
+// _color_temp_to_tint(DISK_COLOR_TEMPERATURE = 6000), render.py:2407-2437, ideal-libm convention
+static void tint_6000(float out[3]) {
+    float t = 6000.0f / 100.0f;
+    out[0] = 1.0f;
+    float g = 0.390082f * (float)log((double)fmaxf(t, 0.0001f)) - 0.631841f;
+    out[1] = fminf(fmaxf(g, 0.0f), 1.0f);
+    float b = 0.543207f * (float)log((double)fmaxf(t - 10.0f, 0.0001f)) - 1.19625f;
+    out[2] = fminf(fmaxf(b, 0.0f), 1.0f);
+}
+
+extern "C" int bhr_version(void) { return 100; }
+
+extern "C" int bhr_create(const bhr_config* cfg, bhr_ctx** out) {
+    if (!cfg || !out) { snprintf(g_bhr_create_error, sizeof(g_bhr_create_error), "null argument"); return BHR_ERR_INVALID; }
+    if (cfg->width <= 0 || cfg->height <= 0 || cfg->step_size <= 0.0f || cfg->r_disk_inner >= cfg->r_disk_outer) {
+        snprintf(g_bhr_create_error, sizeof(g_bhr_create_error), "invalid configuration");
+        return BHR_ERR_INVALID;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        snprintf(g_bhr_create_error, sizeof(g_bhr_create_error), "no CUDA device available (%s); libbhr has no CPU fallback",
+                 cudaGetErrorString(e));
+        return BHR_ERR_CUDA;
+    }
+    bhr_ctx* ctx = (bhr_ctx*)calloc(1, sizeof(bhr_ctx));
+    if (!ctx) return BHR_ERR_NOMEM;
+    ctx->cfg = *cfg;
+    ctx->W = cfg->width; ctx->H = cfg->height;
+    CREATE_CHECK(cudaSetDevice(cfg->device));
+    CREATE_CHECK(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+    ctx->stream = ctx->own_stream;
+    const size_t plane = (size_t)ctx->W * ctx->H;
+    CREATE_CHECK(cudaMalloc(&ctx->bg, plane * 3 * sizeof(float)));
+    CREATE_CHECK(cudaMalloc(&ctx->disk, plane * 3 * sizeof(float)));
+    CREATE_CHECK(cudaMalloc(&ctx->hblur, plane * 3 * sizeof(float)));
+    CREATE_CHECK(cudaMalloc(&ctx->blur, plane * 3 * sizeof(float)));
+    CREATE_CHECK(cudaMalloc(&ctx->final_f32, plane * 3 * sizeof(float)));
+    CREATE_CHECK(cudaMalloc(&ctx->final_u8, plane * 3));
+    CREATE_CHECK(cudaMalloc(&ctx->cls, plane));
+    CREATE_CHECK(cudaMalloc(&ctx->steps, plane * sizeof(int)));
+    CREATE_CHECK(cudaMalloc(&ctx->d_total_steps, sizeof(unsigned long long)));
+    CREATE_CHECK(cudaMalloc(&ctx->d_flare_sums, 3 * sizeof(double)));
+    CREATE_CHECK(cudaMemset(ctx->bg, 0, plane * 3 * sizeof(float)));
+    CREATE_CHECK(cudaMemset(ctx->disk, 0, plane * 3 * sizeof(float)));
+    CREATE_CHECK(cudaMemset(ctx->hblur, 0, plane * 3 * sizeof(float)));
+    CREATE_CHECK(cudaMemset(ctx->blur, 0, plane * 3 * sizeof(float)));
+    CREATE_CHECK(cudaMemset(ctx->cls, 0, plane));
+    CREATE_CHECK(cudaMemset(ctx->steps, 0, plane * sizeof(int)));
+    CREATE_CHECK(cudaMemset(ctx->d_total_steps, 0, sizeof(unsigned long long)));
+    for (int k = 0; k < 6; ++k) CREATE_CHECK(cudaEventCreate(&ctx->ev[k]));
+    tint_6000(ctx->tint);
+    ctx->stats[0] = 0.5f; ctx->stats[1] = 0.5f;    // render.py:3533
+    if (bhr_setup_bloom_tables(ctx) != BHR_OK) {
+        snprintf(g_bhr_create_error, sizeof(g_bhr_create_error), "%s", ctx->err);
+        bhr_destroy(ctx);
+        return BHR_ERR_CUDA;
+    }
+    *out = ctx;
+    return BHR_OK;
+}
+
+extern "C" void bhr_destroy(bhr_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->cfg.device);
+    if (ctx->own_stream) { cudaStreamSynchronize(ctx->own_stream); }
+    void* ptrs[] = {ctx->sky, ctx->mips, ctx->tex_staging, ctx->bg, ctx->disk, ctx->hblur, ctx->blur, ctx->final_f32,
+                    ctx->final_u8, ctx->cls, ctx->steps, ctx->d_total_steps, ctx->d_flare_sums, ctx->d_wtab, ctx->d_wsum_x,
+                    ctx->d_wsum_y, ctx->comp, ctx->edge, ctx->omega_rows, ctx->row_stats, ctx->d_entities};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    for (int k = 0; k < 6; ++k) if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    free(ctx);
+}
+
+extern "C" const char* bhr_last_error(const bhr_ctx* ctx) { return ctx ? ctx->err : g_bhr_create_error; }
+
+extern "C" int bhr_set_stream(bhr_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return BHR_ERR_INVALID;
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return BHR_OK;
+}
+
+extern "C" int bhr_synchronize(bhr_ctx* ctx) {
+    if (!ctx) return BHR_ERR_INVALID;
+    BHR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return BHR_OK;
+}
+
+extern "C" int bhr_set_lens_flare(bhr_ctx* ctx, int enabled) {
+    if (!ctx) return BHR_ERR_INVALID;
+    ctx->cfg.lens_flare = enabled ? 1 : 0;
+    return BHR_OK;
+}
+
+extern "C" int bhr_set_option(bhr_ctx* ctx, const char* key, double value) {
+    if (!key) return BHR_ERR_INVALID;
+    if (!strcmp(key, "raymarch_mode")) { bhr_raymarch_mode_override = (int)value; return BHR_OK; }
+    if (ctx) snprintf(ctx->err, sizeof(ctx->err), "unknown option %s", key);
+    return BHR_ERR_INVALID;
+}
+
+extern "C" int bhr_bloom_radius(const bhr_ctx* ctx) { return ctx ? ctx->bloom_R : -1; }
+
+static int check_rows(bhr_ctx* ctx, int row0, int row1) {
+    if (row0 < 0 || row1 > ctx->H || row0 > row1) BHR_FAIL(ctx, BHR_ERR_INVALID, "bad row range [%d, %d)", row0, row1);
+    return BHR_OK;
+}
+
+extern "C" int bhr_render_rows_stage1(bhr_ctx* ctx, const bhr_camera* cam, uint32_t flags, int row0, int row1) {
+    if (!ctx || !cam) return BHR_ERR_INVALID;
+    int rc = check_rows(ctx, row0, row1);
+    if (rc) return rc;
+    BHR_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    BHR_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+    rc = bhr_launch_raymarch(ctx, cam, flags, row0, row1);
+    if (rc) return rc;
+    BHR_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+    if (!(flags & BHR_SKIP_BLOOM)) {
+        rc = bhr_launch_bloom_h(ctx, row0, row1);
+        if (rc) return rc;
+    }
+    BHR_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+    return BHR_OK;
+}
+
+extern "C" int bhr_flare_sums(bhr_ctx* ctx, int row0, int row1, double out[3]) {
+    if (!ctx || !out) return BHR_ERR_INVALID;
+    int rc = check_rows(ctx, row0, row1);
+    if (rc) return rc;
+    rc = bhr_launch_flare_sums(ctx, row0, row1);
+    if (rc) return rc;
+    BHR_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_flare_sums, 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    BHR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return BHR_OK;
+}
+
+extern "C" int bhr_render_rows_stage2(bhr_ctx* ctx, uint32_t flags, int row0, int row1, const double* flare_sums) {
+    if (!ctx) return BHR_ERR_INVALID;
+    int rc = check_rows(ctx, row0, row1);
+    if (rc) return rc;
+    BHR_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
+    rc = bhr_launch_bloom_v_composite(ctx, flags, row0, row1, flare_sums);
+    if (rc) return rc;
+    BHR_CUDA(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
+    ctx->ev_valid = 1;
+    return BHR_OK;
+}
+
+extern "C" int bhr_render(bhr_ctx* ctx, const bhr_camera* cam, uint32_t flags, float* out_f32, uint8_t* out_u8) {
+    if (!ctx || !cam) return BHR_ERR_INVALID;
+    int rc = bhr_render_rows_stage1(ctx, cam, flags, 0, ctx->H);
+    if (rc) return rc;
+    double sums[3];
+    const double* psums = nullptr;
+    if (ctx->cfg.lens_flare) {
+        // the flare needs the global brightness centroid before any pixel can be finished
+        rc = bhr_flare_sums(ctx, 0, ctx->H, sums);
+        if (rc) return rc;
+        psums = sums;
+    }
+    rc = bhr_render_rows_stage2(ctx, flags, 0, ctx->H, psums);
+    if (rc) return rc;
+    const size_t n3 = (size_t)ctx->W * ctx->H * 3;
+    if (out_f32) BHR_CUDA(ctx, cudaMemcpyAsync(out_f32, ctx->final_f32, n3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_u8) BHR_CUDA(ctx, cudaMemcpyAsync(out_u8, ctx->final_u8, n3, cudaMemcpyDeviceToHost, ctx->stream));
+    BHR_CUDA(ctx, cudaEventRecord(ctx->ev[5], ctx->stream));
+    if (out_f32 || out_u8) BHR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return BHR_OK;
+}
+
+extern "C" int bhr_buffer(bhr_ctx* ctx, int id, void** dev_ptr, size_t* bytes) {
+    if (!ctx || !dev_ptr || !bytes) return BHR_ERR_INVALID;
+    const size_t plane = (size_t)ctx->W * ctx->H;
+    const size_t tex = (size_t)ctx->n_r * ctx->n_phi;
+    switch (id) {
+        case BHR_BUF_BG: *dev_ptr = ctx->bg; *bytes = plane * 12; break;
+        case BHR_BUF_DISK: *dev_ptr = ctx->disk; *bytes = plane * 12; break;
+        case BHR_BUF_HBLUR: *dev_ptr = ctx->hblur; *bytes = plane * 12; break;
+        case BHR_BUF_BLUR: *dev_ptr = ctx->blur; *bytes = plane * 12; break;
+        case BHR_BUF_FINAL: *dev_ptr = ctx->final_f32; *bytes = plane * 12; break;
+        case BHR_BUF_FINAL_U8: *dev_ptr = ctx->final_u8; *bytes = plane * 3; break;
+        case BHR_BUF_CLASS: *dev_ptr = ctx->cls; *bytes = plane; break;
+        case BHR_BUF_STEPS: *dev_ptr = ctx->steps; *bytes = plane * 4; break;
+        case BHR_BUF_DISK_TEX: *dev_ptr = ctx->mips; *bytes = tex * 16; break;
+        case BHR_BUF_DISK_MIPS: *dev_ptr = ctx->mips; *bytes = (size_t)ctx->level_off[BHR_NUM_MIPS] * 16; break;
+        case BHR_BUF_COMP: *dev_ptr = ctx->comp; *bytes = ctx->comp ? tex * BHR_N_COMP * 4 : 0; break;
+        default: BHR_FAIL(ctx, BHR_ERR_INVALID, "unknown buffer id %d", id);
+    }
+    if (!*dev_ptr) BHR_FAIL(ctx, BHR_ERR_STATE, "buffer %d not allocated yet", id);
+    return BHR_OK;
+}
+
+extern "C" int bhr_download(bhr_ctx* ctx, int id, void* host, size_t bytes) {
+    if (!ctx || !host) return BHR_ERR_INVALID;
+    void* d; size_t n;
+    int rc = bhr_buffer(ctx, id, &d, &n);
+    if (rc) return rc;
+    if (bytes > n) BHR_FAIL(ctx, BHR_ERR_INVALID, "buffer %d holds %zu bytes, %zu requested", id, n, bytes);
+    BHR_CUDA(ctx, cudaMemcpyAsync(host, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    BHR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return BHR_OK;
+}
+
+extern "C" int bhr_last_total_steps(bhr_ctx* ctx, uint64_t* out) {
+    if (!ctx || !out) return BHR_ERR_INVALID;
+    unsigned long long v = 0;
+    BHR_CUDA(ctx, cudaMemcpyAsync(&v, ctx->d_total_steps, sizeof(v), cudaMemcpyDeviceToHost, ctx->stream));
+    BHR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = v;
+    return BHR_OK;
+}
+
+extern "C" int bhr_last_stage_ms(bhr_ctx* ctx, float out[5]) {
+    if (!ctx || !out) return BHR_ERR_INVALID;
+    if (!ctx->ev_valid) BHR_FAIL(ctx, BHR_ERR_STATE, "no frame rendered yet");
+    BHR_CUDA(ctx, cudaEventSynchronize(ctx->ev[4]));
+    BHR_CUDA(ctx, cudaEventElapsedTime(&out[0], ctx->ev[0], ctx->ev[1]));   // ray march
+    BHR_CUDA(ctx, cudaEventElapsedTime(&out[1], ctx->ev[1], ctx->ev[2]));   // bloom H
+    BHR_CUDA(ctx, cudaEventElapsedTime(&out[2], ctx->ev[3], ctx->ev[4]));   // bloom V + composite (+ flare)
+    BHR_CUDA(ctx, cudaEventElapsedTime(&out[3], ctx->ev[2], ctx->ev[3]));   // flare reduction / halo gap
+    BHR_CUDA(ctx, cudaEventElapsedTime(&out[4], ctx->ev[0], ctx->ev[4]));   // total
+    return BHR_OK;
+}
+
+// pinned host memory for zero-staging D2H of frames
+extern "C" int bhr_host_alloc(size_t bytes, void** out) {
+    if (!out) return BHR_ERR_INVALID;
+    return cudaHostAlloc(out, bytes, cudaHostAllocDefault) == cudaSuccess ? BHR_OK : BHR_ERR_NOMEM;
+}
+extern "C" int bhr_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? BHR_OK : BHR_ERR_CUDA; }
+
+// ---------------------------------------------------------------------------------------------
+// FP32 throughput probe (roofline denominator of the integrator)
+// ---------------------------------------------------------------------------------------------
+namespace {
+template <int MODE> __global__ void __launch_bounds__(256) fma_probe(float* out, int iters) {
+    float x[8]; float2 v[8];
+    for (int j = 0; j < 8; ++j) { x[j] = threadIdx.x * 1e-3f + j; v[j] = make_float2(x[j], x[j] + 0.5f); }
+    const float m = 0.999f, c = 1e-3f; const float2 m2 = make_float2(0.999f, 1.001f), c2 = make_float2(1e-3f, 2e-3f);
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (MODE == 0) x[j] = fmaf(x[j], m, c);
+                else v[j] = __ffma2_rn(v[j], m2, c2);
+            }
+        }
+    }
+    float s = 0;
+    for (int j = 0; j < 8; ++j) s += x[j] + v[j].x + v[j].y;
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+}  // namespace
+
+extern "C" int bhr_measure_fp32_peak(int device, int mode, double* tflops) {
+    if (!tflops) return BHR_ERR_INVALID;
+    if (cudaSetDevice(device) != cudaSuccess) return BHR_ERR_CUDA;
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    const int grid = sms * 8, iters = 20000;
+    float* out = nullptr;
+    if (cudaMalloc(&out, sizeof(float) * grid * 256) != cudaSuccess) return BHR_ERR_NOMEM;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int r = 0; r < 6; ++r) {
+        cudaEventRecord(e0);
+        if (mode == 0) fma_probe<0><<<grid, 256>>>(out, iters); else fma_probe<1><<<grid, 256>>>(out, iters);
+        cudaEventRecord(e1); cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        if (r > 0 && ms < best) best = ms;
+    }
+    cudaError_t e = cudaGetLastError();
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+    if (e != cudaSuccess) return BHR_ERR_CUDA;
+    const double fma = (double)grid * 256 * iters * 64.0 * (mode == 0 ? 1.0 : 2.0);
+    *tflops = fma * 2.0 / (best * 1e-3) / 1e12;
+    return BHR_OK;
+}

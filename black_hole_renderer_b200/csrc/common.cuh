@@ -1,0 +1,101 @@
+// common.cuh -- context layout and small helpers shared by the libbhr.so translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/bhr.h"
+
+#define BHR_NUM_MIPS 5          // base + 4 levels, render.py:2239
+#define BHR_N_COMP 13           // component planes, render.py:2328-2332
+
+// Per-frame parameters of the ray-march kernel (kernel argument, lives in constant bank 0).
+struct RayParams {
+    int W, H;                   // full frame
+    int row0, row1;             // rows traced by this launch
+    float cp[3], cr[3], cu[3], cf[3];
+    float pw, ph;
+    float r_esc, r_esc2;
+    float h_base, r_in, r_out, t_offset;
+    float tilt_rad, tan_t, sin_t, cos_t;
+    int max_iter;
+    float max_affine;
+    int aa_mode;                // sample through the mip pyramid (anti_alias && !skip_diff)
+    float aa_strength;
+    float tint[3];              // _color_temp_to_tint(6000 K), render.py:2515
+    const float4* sky;          // (sky_h, sky_w) RGBx
+    int sky_w, sky_h;
+    const float4* mips;         // compact pyramid of RGBA texels
+    int dtex_w, dtex_h;
+    unsigned int level_off[BHR_NUM_MIPS];
+    float* bg;                  // planar 3 x (H, W)
+    float* disk;                // planar 3 x (H, W)
+    size_t plane;               // W * H
+    uint8_t* cls;               // (H, W) or nullptr
+    int* steps;                 // (H, W) or nullptr
+    unsigned long long* total_steps; // or nullptr
+};
+
+struct bhr_ctx {
+    bhr_config cfg;
+    int W, H;
+    cudaStream_t stream, own_stream;
+    char err[512];
+
+    float4* sky; int sky_w, sky_h;
+    float4* mips; int n_r, n_phi; unsigned int level_off[BHR_NUM_MIPS + 1];
+    float* tex_staging;         // (n_r, n_phi, 4) upload staging == disk_texture_field
+
+    float *bg, *disk, *hblur, *blur;   // planar 3 x (H, W) each
+    float* final_f32;                  // (H, W, 3)
+    uint8_t* final_u8;                 // (H, W, 3)
+    uint8_t* cls; int* steps;
+    unsigned long long* d_total_steps;
+    double* d_flare_sums;              // {sum B, sum x*B, sum y*B}
+
+    int bloom_R; float sigma_scale;
+    float* d_wtab;                     // 3 x wtab_stride (2R+1 weights + zero padding)
+    int wtab_stride;
+    float* d_wsum_x;                   // 3 x W   in-bounds weight sums (sequential f32 order)
+    float* d_wsum_y;                   // 3 x H
+
+    // disk-texture pipeline
+    float* comp;                       // (13, n_r, n_phi)
+    float *edge, *omega_rows, *row_stats;
+    float stats[2];
+    int bg_ready, az_freq; float az_shear;
+    bhr_entity* d_entities; int entities_cap;
+
+    cudaEvent_t ev[6];
+    int ev_valid;
+    float tint[3];
+};
+
+extern char g_bhr_create_error[512];
+
+#define BHR_CUDA(ctx, call)                                                                      \
+    do {                                                                                         \
+        cudaError_t e_ = (call);                                                                 \
+        if (e_ != cudaSuccess) {                                                                 \
+            snprintf((ctx)->err, sizeof((ctx)->err), "%s:%d: %s: %s", __FILE__, __LINE__, #call, \
+                     cudaGetErrorString(e_));                                                    \
+            return BHR_ERR_CUDA;                                                                 \
+        }                                                                                        \
+    } while (0)
+
+#define BHR_FAIL(ctx, code, ...)                                   \
+    do {                                                           \
+        snprintf((ctx)->err, sizeof((ctx)->err), __VA_ARGS__);     \
+        return (code);                                             \
+    } while (0)
+
+static inline int bhr_div_up(int a, int b) { return (a + b - 1) / b; }
+
+// kernels / launchers implemented in the other translation units
+int bhr_launch_raymarch(bhr_ctx* ctx, const bhr_camera* cam, uint32_t flags, int row0, int row1);
+int bhr_launch_bloom_h(bhr_ctx* ctx, int row0, int row1);
+int bhr_launch_bloom_v_composite(bhr_ctx* ctx, uint32_t flags, int row0, int row1, const double* flare_sums_host);
+int bhr_launch_flare_sums(bhr_ctx* ctx, int row0, int row1);
+int bhr_launch_build_mips(bhr_ctx* ctx, int numpy_order);
+int bhr_setup_bloom_tables(bhr_ctx* ctx);

@@ -1,0 +1,479 @@
+// texture.cu -- skybox / disk-texture uploads, mip pyramid, and the on-device disk-texture
+// pipeline: simplex-FBM background layer, entity layer, compose, noise test hook.
+//
+// Replaces (reference = render.py):
+//   generate_disk_mipmaps + padded upload (1113-1125, 2239-2251) and the mip kernels (3261-3281)
+//   _simplex_noise_3d / _fbm_3d / _generate_background_kernel (2642-2785, 3332-3451)
+//   accumulate_entity_layer's numpy loops + staging copy kernel (3564-3653, 3455-3471)
+//   _compose_disk_texture_kernel (3169-3257), _noise_eval_kernel (3305-3326)
+#include <math.h>
+
+#include "common.cuh"
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// uploads
+// ---------------------------------------------------------------------------------------------
+__global__ void pack_rgb_kernel(const float* __restrict__ rgb, float4* __restrict__ out, size_t n) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = make_float4(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2], 0.0f);
+}
+
+// one mip level from the previous one: 2x2 mean.  numpy_order selects the summation order of
+// generate_disk_mipmaps ((0,0)+(1,0)+(0,1)+(1,1), render.py:1122-1123) instead of the mip
+// kernel's ((0,0)+(0,1)+(1,0)+(1,1), render.py:3277-3280).
+__global__ void mip_down_kernel(const float4* __restrict__ src, float4* __restrict__ dst, int dh, int dw,
+                                int src_pitch, int numpy_order) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y * blockDim.y + threadIdx.y;
+    if (c >= dw || r >= dh) return;
+    float4 a = src[(size_t)(2 * r) * src_pitch + 2 * c], b = src[(size_t)(2 * r) * src_pitch + 2 * c + 1];
+    float4 cc = src[(size_t)(2 * r + 1) * src_pitch + 2 * c], d = src[(size_t)(2 * r + 1) * src_pitch + 2 * c + 1];
+    float4 o;
+    if (numpy_order) {
+        o.x = __fdiv_rn(__fadd_rn(__fadd_rn(__fadd_rn(a.x, cc.x), b.x), d.x), 4.0f);
+        o.y = __fdiv_rn(__fadd_rn(__fadd_rn(__fadd_rn(a.y, cc.y), b.y), d.y), 4.0f);
+        o.z = __fdiv_rn(__fadd_rn(__fadd_rn(__fadd_rn(a.z, cc.z), b.z), d.z), 4.0f);
+        o.w = __fdiv_rn(__fadd_rn(__fadd_rn(__fadd_rn(a.w, cc.w), b.w), d.w), 4.0f);
+    } else {
+        o.x = __fdiv_rn(__fadd_rn(__fadd_rn(__fadd_rn(a.x, b.x), cc.x), d.x), 4.0f);
+        o.y = __fdiv_rn(__fadd_rn(__fadd_rn(__fadd_rn(a.y, b.y), cc.y), d.y), 4.0f);
+        o.z = __fdiv_rn(__fadd_rn(__fadd_rn(__fadd_rn(a.z, b.z), cc.z), d.z), 4.0f);
+        o.w = __fdiv_rn(__fadd_rn(__fadd_rn(__fadd_rn(a.w, b.w), cc.w), d.w), 4.0f);
+    }
+    dst[(size_t)r * dw + c] = o;
+}
+
+// ---------------------------------------------------------------------------------------------
+// 3-D simplex noise + FBM, render.py:2642-2785
+// ---------------------------------------------------------------------------------------------
+__constant__ unsigned char c_perm[256] = {
+    151, 160, 137, 91, 90, 15, 131, 13, 201, 95, 96, 53, 194, 233, 7, 225, 140, 36, 103, 30, 69,
+    142, 8, 99, 37, 240, 21, 10, 23, 190, 6, 148, 247, 120, 234, 75, 0, 26, 197, 62, 94, 252, 219,
+    203, 117, 35, 11, 32, 57, 177, 33, 88, 237, 149, 56, 87, 174, 20, 125, 136, 171, 168, 68, 175,
+    74, 165, 71, 134, 139, 48, 27, 166, 77, 146, 158, 231, 83, 111, 229, 122, 60, 211, 133, 230,
+    220, 105, 92, 41, 55, 46, 245, 40, 244, 102, 143, 54, 65, 25, 63, 161, 1, 216, 80, 73, 209,
+    76, 132, 187, 208, 89, 18, 169, 200, 196, 135, 130, 116, 188, 159, 86, 164, 100, 109, 198,
+    173, 186, 3, 64, 52, 217, 226, 250, 124, 123, 5, 202, 38, 147, 118, 126, 255, 82, 85, 212,
+    207, 206, 59, 227, 47, 16, 58, 17, 182, 189, 28, 42, 223, 183, 170, 213, 119, 248, 152, 2, 44,
+    154, 163, 70, 221, 153, 101, 155, 167, 43, 172, 9, 129, 22, 39, 253, 19, 98, 108, 110, 79,
+    113, 224, 232, 178, 185, 112, 104, 218, 246, 97, 228, 251, 34, 242, 193, 238, 210, 144, 12,
+    191, 179, 162, 241, 81, 51, 145, 235, 249, 14, 239, 107, 49, 192, 214, 31, 181, 199, 106,
+    157, 184, 84, 204, 176, 115, 121, 50, 45, 127, 4, 150, 254, 138, 236, 205, 93, 222, 114, 67,
+    29, 24, 72, 243, 141, 128, 195, 78, 66, 215, 61, 156, 180};
+
+// the kernels read the permutation from shared memory (divergent byte lookups: constant memory
+// would serialise them)
+struct Perm { const unsigned char* t; __device__ __forceinline__ int operator()(int i) const { return t[i & 255]; } };
+
+__device__ __forceinline__ float grad3_dot(int hash, float x, float y, float z) {
+    int h = hash % 12;
+    float u = h < 8 ? x : y;
+    float v = h < 4 ? y : z;      // the (h == 12 || h == 14) arm of render.py:2657 is unreachable
+    return ((h & 1) == 0 ? u : -u) + ((h & 2) == 0 ? v : -v);
+}
+
+__device__ float simplex3(const Perm& perm, float x, float y, float z) {
+    const float F3 = (float)(1.0 / 3.0), G3 = (float)(1.0 / 6.0);
+    const float G3x2 = (float)(2.0 * (1.0 / 6.0)), G3x3 = (float)(3.0 * (1.0 / 6.0));
+    // the skew / unskew arithmetic decides which lattice cell a point falls in; keep it exactly
+    // rounded (no FMA contraction) so the cell choice matches the reference's f32 evaluation
+    float s = __fmul_rn(__fadd_rn(__fadd_rn(x, y), z), F3);
+    float fi = floorf(__fadd_rn(x, s)), fj = floorf(__fadd_rn(y, s)), fk = floorf(__fadd_rn(z, s));
+    int i = (int)fi, j = (int)fj, k = (int)fk;
+    float t = __fmul_rn((float)(i + j + k), G3);
+    float x0 = __fsub_rn(x, __fsub_rn(fi, t)), y0 = __fsub_rn(y, __fsub_rn(fj, t)), z0 = __fsub_rn(z, __fsub_rn(fk, t));
+    int i1, j1, k1, i2, j2, k2;
+    if (x0 >= y0) {
+        if (y0 >= z0) { i1 = 1; j1 = 0; k1 = 0; i2 = 1; j2 = 1; k2 = 0; }
+        else if (x0 >= z0) { i1 = 1; j1 = 0; k1 = 0; i2 = 1; j2 = 0; k2 = 1; }
+        else { i1 = 0; j1 = 0; k1 = 1; i2 = 1; j2 = 0; k2 = 1; }
+    } else {
+        if (y0 < z0) { i1 = 0; j1 = 0; k1 = 1; i2 = 0; j2 = 1; k2 = 1; }
+        else if (x0 < z0) { i1 = 0; j1 = 1; k1 = 0; i2 = 0; j2 = 1; k2 = 1; }
+        else { i1 = 0; j1 = 1; k1 = 0; i2 = 1; j2 = 1; k2 = 0; }
+    }
+    float x1 = __fadd_rn(__fsub_rn(x0, (float)i1), G3), y1 = __fadd_rn(__fsub_rn(y0, (float)j1), G3), z1 = __fadd_rn(__fsub_rn(z0, (float)k1), G3);
+    float x2 = __fadd_rn(__fsub_rn(x0, (float)i2), G3x2), y2 = __fadd_rn(__fsub_rn(y0, (float)j2), G3x2), z2 = __fadd_rn(__fsub_rn(z0, (float)k2), G3x2);
+    float x3 = __fadd_rn(__fsub_rn(x0, 1.0f), G3x3), y3 = __fadd_rn(__fsub_rn(y0, 1.0f), G3x3), z3 = __fadd_rn(__fsub_rn(z0, 1.0f), G3x3);
+    int ii = i & 255, jj = j & 255, kk = k & 255;
+    int gi0 = perm(ii + perm(jj + perm(kk)));
+    int gi1 = perm(ii + i1 + perm(jj + j1 + perm(kk + k1)));
+    int gi2 = perm(ii + i2 + perm(jj + j2 + perm(kk + k2)));
+    int gi3 = perm(ii + 1 + perm(jj + 1 + perm(kk + 1)));
+    float n = 0.0f;
+    float t0 = __fsub_rn(__fsub_rn(__fsub_rn(0.6f, __fmul_rn(x0, x0)), __fmul_rn(y0, y0)), __fmul_rn(z0, z0));
+    if (t0 >= 0.0f) { t0 = __fmul_rn(t0, t0); n = __fadd_rn(n, __fmul_rn(__fmul_rn(t0, t0), grad3_dot(gi0, x0, y0, z0))); }
+    float t1 = __fsub_rn(__fsub_rn(__fsub_rn(0.6f, __fmul_rn(x1, x1)), __fmul_rn(y1, y1)), __fmul_rn(z1, z1));
+    if (t1 >= 0.0f) { t1 = __fmul_rn(t1, t1); n = __fadd_rn(n, __fmul_rn(__fmul_rn(t1, t1), grad3_dot(gi1, x1, y1, z1))); }
+    float t2 = __fsub_rn(__fsub_rn(__fsub_rn(0.6f, __fmul_rn(x2, x2)), __fmul_rn(y2, y2)), __fmul_rn(z2, z2));
+    if (t2 >= 0.0f) { t2 = __fmul_rn(t2, t2); n = __fadd_rn(n, __fmul_rn(__fmul_rn(t2, t2), grad3_dot(gi2, x2, y2, z2))); }
+    float t3 = __fsub_rn(__fsub_rn(__fsub_rn(0.6f, __fmul_rn(x3, x3)), __fmul_rn(y3, y3)), __fmul_rn(z3, z3));
+    if (t3 >= 0.0f) { t3 = __fmul_rn(t3, t3); n = __fadd_rn(n, __fmul_rn(__fmul_rn(t3, t3), grad3_dot(gi3, x3, y3, z3))); }
+    return __fmul_rn(32.0f, n);
+}
+
+__device__ float fbm3(const Perm& perm, float x, float y, float z, int octaves, float persistence, float lacunarity) {
+    float value = 0.0f, amplitude = 1.0f, freq = 1.0f;
+    for (int o = 0; o < octaves; ++o) {
+        value = __fadd_rn(value, __fmul_rn(amplitude, simplex3(perm, __fmul_rn(x, freq), __fmul_rn(y, freq), __fmul_rn(z, freq))));
+        amplitude = __fmul_rn(amplitude, persistence);
+        freq = __fmul_rn(freq, lacunarity);
+    }
+    return value;
+}
+
+__device__ __forceinline__ float unit_fbm(const Perm& perm, float x, float y, float z, int o, float p) {
+    return fminf(fmaxf(__fadd_rn(0.5f, __fmul_rn(0.5f, fbm3(perm, x, y, z, o, p, 2.0f))), 0.0f), 1.0f);
+}
+__device__ __forceinline__ float m_(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float a_(float a, float b) { return __fadd_rn(a, b); }
+
+__global__ void __launch_bounds__(256) noise_eval_kernel(const float* __restrict__ coords, int n, int mode, int octaves,
+                                                         float persistence, float lacunarity, float* __restrict__ out) {
+    __shared__ unsigned char sperm[256];
+    sperm[threadIdx.x] = c_perm[threadIdx.x];
+    __syncthreads();
+    Perm perm{sperm};
+    int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    float x = coords[3 * i], y = coords[3 * i + 1], z = coords[3 * i + 2];
+    out[i] = mode == 0 ? simplex3(perm, x, y, z) : fbm3(perm, x, y, z, octaves, persistence, lacunarity);
+}
+
+// render.py:3332-3451; writes comp planes 0,1,2,3,4,11,12.  42 simplex evaluations per texel.
+// The cos/sin of the Keplerian-rotated angle feed noise coordinates scaled by up to 800, so
+// they are evaluated in double and rounded once (the oracle's ideal-libm convention).
+__global__ void __launch_bounds__(256) background_kernel(float* __restrict__ comp, int n_r, int n_phi, int az_freq,
+                                                         float az_shear, float r_inner, float r_outer, float t) {
+    __shared__ unsigned char sperm[256];
+    sperm[threadIdx.x] = c_perm[threadIdx.x];
+    __syncthreads();
+    Perm perm{sperm};
+    const size_t plane = (size_t)n_r * n_phi;
+    const size_t o = blockIdx.x * (size_t)256 + threadIdx.x;
+    if (o >= plane) return;
+    const int ri = (int)(o / n_phi), pi = (int)(o % n_phi);
+    const float r = __fdiv_rn((float)ri, (float)n_r);
+    const float phi = m_(__fdiv_rn((float)pi, (float)n_phi), 6.2831855f);
+    const float r_phys = a_(r_inner, m_(__fsub_rn(r_outer, r_inner), r));
+    const float omega = __fsqrt_rn(__fdiv_rn(0.5f, a_(m_(m_(r_phys, r_phys), r_phys), 1e-6f)));
+    const float phi_rot = a_(phi, m_(omega, t));
+    const float cx = (float)cos((double)phi_rot), cy = (float)sin((double)phi_rot);
+
+    float decay = (float)pow((double)fmaxf(__fsub_rn(1.0f, r), 0.0f), (double)1.3f);
+    float tb = unit_fbm(perm, m_(cx, 8.0f), m_(cy, 8.0f), a_(m_(r, 8.0f), m_(t, 0.05f)), 4, 0.6f);
+    comp[0 * plane + o] = m_(m_(decay, a_(0.85f, m_(0.15f, tb))), 0.25f);
+    comp[1 * plane + o] = 0.0f;
+    comp[2 * plane + o] = 0.0f;
+
+    float t_coarse = m_(unit_fbm(perm, m_(cx, 8.0f), m_(cy, 8.0f), a_(m_(r, 4.0f), m_(t, 0.06f)), 3, 0.45f), 0.08f);
+    float t_mid = m_(unit_fbm(perm, m_(cx, 24.0f), m_(cy, 24.0f), a_(m_(r, 12.0f), m_(t, 0.08f)), 4, 0.45f), 0.15f);
+    float t_fine = m_(unit_fbm(perm, m_(cx, 80.0f), m_(cy, 80.0f), a_(m_(r, 40.0f), m_(t, 0.1f)), 5, 0.45f), 0.25f);
+    float t_extra = m_(unit_fbm(perm, m_(cx, 200.0f), m_(cy, 200.0f), a_(m_(r, 100.0f), m_(t, 0.12f)), 4, 0.4f), 0.22f);
+    float t_ultra = m_(unit_fbm(perm, m_(cx, 400.0f), m_(cy, 400.0f), a_(m_(r, 200.0f), m_(t, 0.15f)), 3, 0.35f), 0.18f);
+    float t_pixel = m_(fminf(fmaxf(simplex3(perm, m_(cx, 800.0f), m_(cy, 800.0f), a_(m_(r, 400.0f), m_(t, 0.2f))), 0.0f), 1.0f), 0.12f);
+    float turb = fminf(fmaxf(a_(a_(a_(a_(a_(t_coarse, t_mid), t_fine), t_extra), t_ultra), t_pixel), 0.0f), 1.0f);
+    comp[3 * plane + o] = turb;
+    comp[4 * plane + o] = m_(0.05f, turb);
+
+    float shear = m_((float)pow((double)r, (double)1.2f), az_shear);
+    float az_wave = a_(0.5f, m_(0.5f, (float)sin((double)m_(a_(phi_rot, shear), (float)az_freq))));
+    float az_n = unit_fbm(perm, m_(cx, 3.0f), m_(cy, 3.0f), a_(m_(r, 3.0f), m_(t, 0.04f)), 3, 0.5f);
+    comp[11 * plane + o] = m_(az_wave, az_n);
+
+    float d_coarse = m_(unit_fbm(perm, m_(cx, 8.0f), m_(cy, 8.0f), a_(m_(r, 4.0f), m_(t, 0.003f)), 3, 0.5f), 0.05f);
+    float d_mid = m_(unit_fbm(perm, m_(cx, 32.0f), m_(cy, 32.0f), a_(m_(r, 16.0f), m_(t, 0.005f)), 3, 0.5f), 0.15f);
+    float d_fine = m_(unit_fbm(perm, m_(cx, 100.0f), m_(cy, 100.0f), a_(m_(r, 50.0f), m_(t, 0.006f)), 4, 0.45f), 0.30f);
+    float d_extra = m_(unit_fbm(perm, m_(cx, 250.0f), m_(cy, 250.0f), a_(m_(r, 125.0f), m_(t, 0.008f)), 4, 0.4f), 0.30f);
+    float d_pixel = m_(fminf(fmaxf(simplex3(perm, m_(cx, 500.0f), m_(cy, 500.0f), a_(m_(r, 250.0f), m_(t, 0.01f))), 0.0f), 1.0f), 0.20f);
+    float raw = m_(a_(a_(a_(a_(d_coarse, d_mid), d_fine), d_extra), d_pixel), 1.4f);
+    raw = fminf(fmaxf(raw, 0.05f), 1.0f);
+    float preserve = a_(0.6f, m_(0.4f, r));
+    comp[12 * plane + o] = fminf(fmaxf(m_(raw, preserve), 0.1f), 1.0f);
+}
+
+// ---------------------------------------------------------------------------------------------
+// entity layer, render.py:3564-3653: one thread per texel sums, in list order, every entity
+// whose row range contains the texel's row (so the f32 accumulation order equals numpy's).
+//   filament p[]: 0 source_phi, 1 base_r, 2 inv_2sigma_r_sq, 3 inv_2sigma_phi_sq, 4 scale_d, 5 scale_t
+//   hotspot  p[]: 0 h_phi, 1 h_r, 2 h_phi_width, 3 h_r_width, 4 h_intensity        (temp = 0.12 * density)
+//   rt_spike p[]: 0 rt_phi, 1 rt_r_base, 2 rt_phi_width, 3 rt_r_length, 4 rt_intensity, 5 rt_delta_T
+// planes: filament -> comp[5], comp[6]; rt_spike -> comp[7], comp[8]; hotspot -> comp[9], comp[10]
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float py_modf32(float a, float b) {
+    float m = fmodf(a, b);
+    if (m != 0.0f && ((m < 0.0f) != (b < 0.0f))) m += b;
+    return m;
+}
+
+__global__ void __launch_bounds__(256) entity_accumulate_kernel(float* __restrict__ comp, int n_r, int n_phi,
+                                                                const bhr_entity* __restrict__ ents, int n_ent,
+                                                                const float* __restrict__ omega_rows) {
+    const size_t plane = (size_t)n_r * n_phi;
+    const size_t o = blockIdx.x * (size_t)256 + threadIdx.x;
+    if (o >= plane) return;
+    const int ri = (int)(o / n_phi), pi = (int)(o % n_phi);
+    const double TWO_PI = 6.283185307179586;
+    const double r_norm = (ri == n_r - 1) ? 1.0 : (double)ri * (1.0 / (double)(n_r - 1));   // np.linspace(0, 1, n_r)
+    const double phi_step = TWO_PI / (double)n_phi;                                           // linspace(endpoint=False)
+    const float om = omega_rows[ri];
+    float acc[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+    for (int e = 0; e < n_ent; ++e) {
+        const bhr_entity& E = ents[e];
+        if (ri < E.row_begin || ri >= E.row_end) continue;
+        if (E.kind == 0) {
+            double dr = r_norm - E.p[1];
+            double r_w = exp(-(dr * dr) * E.p[2]);
+            // center = (source_phi - omega[ri] * age) % 2pi evaluates in float32 in the reference
+            // (np.float32 scalar with weak Python floats), render.py:3633
+            float center = py_modf32(__fsub_rn((float)E.p[0], __fmul_rn(om, (float)E.age)), 6.2831855f);
+            double d_phi = (double)pi * phi_step - (double)center;
+            d_phi = d_phi - TWO_PI * rint(d_phi / TWO_PI);
+            double prof = exp(-d_phi * d_phi * E.p[3]);
+            acc[0] = (float)((double)acc[0] + prof * (E.p[4] * r_w));
+            acc[1] = (float)((double)acc[1] + prof * (E.p[5] * r_w));
+        } else {
+            // shift = int(age * omega[ri] / (2 pi) * n_phi) in float32, render.py:3645
+            float sf = __fmul_rn(__fdiv_rn(__fmul_rn((float)E.age, om), 6.2831855f), (float)n_phi);
+            int shift = (int)sf;
+            int src = (pi + shift) % n_phi;
+            if (src < 0) src += n_phi;
+            double phi = (double)src * phi_step;
+            double kappa = 1.5 / (E.p[2] * E.p[2]);
+            double phi_prof = exp(kappa * (cos(phi - E.p[0]) - 1.0));
+            const float alpha = (float)E.scale;
+            if (E.kind == 1) {
+                double rd = r_norm - E.p[1];
+                double q = rd / (E.p[3] + 1e-8);
+                double r_prof = exp(-0.5 * (q * q));
+                float dens = (float)(phi_prof * r_prof * E.p[4]);
+                float temp = __fmul_rn(dens, 0.12f);
+                dens = fminf(fmaxf(dens, 0.0f), 1.0f);
+                temp = fminf(fmaxf(temp, 0.0f), 1.0f);
+                acc[4] = __fadd_rn(acc[4], __fmul_rn(dens, alpha));
+                acc[5] = __fadd_rn(acc[5], __fmul_rn(temp, alpha));
+            } else {
+                double rd = r_norm - E.p[1];
+                double fo = fmin(fmax(E.p[3] * 2 - rd, 0.0), 1.0);
+                double fi = fmin(fmax(rd / (E.p[3] * 0.3 + 1e-8), 0.0), 1.0);
+                double q = rd / (E.p[3] * 0.4 + 1e-8);
+                double r_prof = exp(-0.5 * (q * q)) * fo * fi;
+                float dens = (float)(phi_prof * r_prof * E.p[4]);
+                float temp = __fmul_rn(dens, (float)E.p[5]);
+                dens = fminf(fmaxf(dens, 0.0f), 1.0f);
+                acc[2] = __fadd_rn(acc[2], __fmul_rn(dens, alpha));
+                acc[3] = __fadd_rn(acc[3], __fmul_rn(temp, alpha));
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) comp[(5 + k) * plane + o] = acc[k];
+}
+
+// ---------------------------------------------------------------------------------------------
+// compose, render.py:3169-3257 (+ _color_temp_to_tint, 2407-2437); writes mip level 0 directly
+// ---------------------------------------------------------------------------------------------
+__device__ void color_temp_to_tint(float temp, float& r, float& g, float& b) {
+    float t = __fdiv_rn(temp, 100.0f);
+    r = 1.0f; b = 1.0f;
+    if (t > 66.0f) r = fminf(fmaxf(m_(1.292936f, (float)pow((double)fmaxf(__fsub_rn(t, 60.0f), 0.0001f), (double)-0.1332047592f)), 0.0f), 1.0f);
+    if (t <= 66.0f) g = fminf(fmaxf(__fsub_rn(m_(0.390082f, (float)log((double)fmaxf(t, 0.0001f))), 0.631841f), 0.0f), 1.0f);
+    else g = fminf(fmaxf(m_(1.129891f, (float)pow((double)fmaxf(__fsub_rn(t, 60.0f), 0.0001f), (double)-0.0755148492f)), 0.0f), 1.0f);
+    if (t < 66.0f) {
+        if (t <= 19.0f) b = 0.0f;
+        else b = fminf(fmaxf(__fsub_rn(m_(0.543207f, (float)log((double)fmaxf(__fsub_rn(t, 10.0f), 0.0001f))), 1.19625f), 0.0f), 1.0f);
+    }
+}
+
+__global__ void __launch_bounds__(256) compose_kernel(const float* __restrict__ comp, const float* __restrict__ omega,
+                                                      const float* __restrict__ edge, float p98, float sscale,
+                                                      const float* __restrict__ row_stats, int n_r, int n_phi,
+                                                      float t_offset, int enable_rt, float color_temp,
+                                                      float4* __restrict__ tex) {
+    const size_t plane = (size_t)n_r * n_phi;
+    const size_t idx = blockIdx.x * (size_t)256 + threadIdx.x;
+    if (idx >= plane) return;
+    const int ri = (int)(idx / n_phi), pi = (int)(idx % n_phi);
+    const float t_factor = __fdiv_rn(__fsub_rn(color_temp, 4500.0f), 3800.0f);
+    const float T_min = a_(2000.0f, m_(t_factor, 1000.0f)), T_max = a_(9000.0f, m_(t_factor, 3000.0f));
+    const float rt_w = enable_rt == 0 ? 0.0f : 0.20f;
+    int shift = (int)m_(__fdiv_rn(m_(t_offset, omega[ri]), 6.2831855f), (float)n_phi);
+    int src = (pi + shift) % n_phi;
+    if (src < 0) src += n_phi;
+    const size_t o = (size_t)ri * n_phi + src;
+    float tb = comp[o], sp = comp[plane + o], sp_t = comp[2 * plane + o], turb = comp[3 * plane + o];
+    float turb_t = comp[4 * plane + o], arc = comp[5 * plane + o], arc_t = comp[6 * plane + o];
+    float rt = comp[7 * plane + o], rt_t = comp[8 * plane + o], hs = comp[9 * plane + o], hs_t = comp[10 * plane + o];
+    float az = comp[11 * plane + o], dm = comp[12 * plane + o];
+    float density = m_(m_(a_(a_(a_(a_(a_(0.15f, m_(0.10f, sp)), m_(0.30f, turb)), m_(0.20f, hs)), m_(0.30f, arc)), m_(rt_w, rt)), dm), edge[ri]);
+    density = fminf(fmaxf(__fdiv_rn(density, a_(p98, 1e-6f)), 0.0f), 1.0f);
+    float ts = m_(a_(a_(a_(a_(sp_t, turb_t), arc_t), rt_t), hs_t), dm);
+    float ts_scaled = fminf(fmaxf(m_(__fdiv_rn(ts, a_(sscale, 1e-6f)), 0.8f), 0.0f), 1.2f);
+    float max_r = row_stats[2 * ri], p70_r = row_stats[2 * ri + 1];
+    float tbc = fminf(fminf(tb, fmaxf(p70_r, 0.05f)), max_r);
+    float temperature = fminf(fmaxf(fmaxf(tbc, ts_scaled), 0.0f), 1.0f);
+    float ta = fminf(fmaxf(m_(temperature, a_(0.9f, m_(0.25f, az))), 0.0f), 1.0f);
+    float T_K = a_(T_min, m_(ta, __fsub_rn(T_max, T_min)));
+    float br, bg, bb;
+    color_temp_to_tint(T_K, br, bg, bb);
+    float bb_b = fminf(bb, br);
+    float lum = fminf(fmaxf(__fsqrt_rn(ta), 0.0f), 1.0f);
+    tex[idx] = make_float4(fminf(fmaxf(m_(br, lum), 0.0f), 1.0f), fminf(fmaxf(m_(bg, lum), 0.0f), 1.0f),
+                           fminf(fmaxf(m_(bb_b, lum), 0.0f), 1.0f), density);
+}
+
+}  // namespace
+
+int bhr_launch_build_mips(bhr_ctx* ctx, int numpy_order) {
+    int h = ctx->n_r, w = ctx->n_phi;
+    for (int lev = 1; lev < BHR_NUM_MIPS; ++lev) {
+        int dh = h / 2, dw = w / 2;
+        dim3 block(32, 8), grid(bhr_div_up(dw, 32), bhr_div_up(dh, 8));
+        mip_down_kernel<<<grid, block, 0, ctx->stream>>>(ctx->mips + ctx->level_off[lev - 1], ctx->mips + ctx->level_off[lev],
+                                                         dh, dw, w, numpy_order);
+        h = dh; w = dw;
+    }
+    BHR_CUDA(ctx, cudaGetLastError());
+    return BHR_OK;
+}
+
+extern "C" int bhr_upload_skybox(bhr_ctx* ctx, const float* rgb, int h, int w) {
+    if (!ctx || !rgb || h <= 0 || w <= 0) return BHR_ERR_INVALID;
+    size_t n = (size_t)h * w;
+    float* staging = nullptr;
+    if (ctx->sky) { cudaFree(ctx->sky); ctx->sky = nullptr; }
+    BHR_CUDA(ctx, cudaMalloc(&ctx->sky, n * sizeof(float4)));
+    BHR_CUDA(ctx, cudaMalloc(&staging, n * 3 * sizeof(float)));
+    BHR_CUDA(ctx, cudaMemcpyAsync(staging, rgb, n * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    pack_rgb_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(staging, ctx->sky, n);
+    BHR_CUDA(ctx, cudaGetLastError());
+    BHR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(staging);
+    ctx->sky_w = w; ctx->sky_h = h;
+    return BHR_OK;
+}
+
+static int ensure_disk_storage(bhr_ctx* ctx, int n_r, int n_phi) {
+    if (ctx->mips) {
+        if (n_r != ctx->n_r || n_phi != ctx->n_phi)
+            BHR_FAIL(ctx, BHR_ERR_INVALID, "Texture size mismatch: expected %dx%d, got %dx%d", ctx->n_r, ctx->n_phi, n_r, n_phi);
+        return BHR_OK;
+    }
+    if (n_r < 16 || n_phi < 16) BHR_FAIL(ctx, BHR_ERR_INVALID, "disk texture must be at least 16x16 (5 mip levels)");
+    ctx->n_r = n_r; ctx->n_phi = n_phi;
+    unsigned int off = 0;
+    int h = n_r, w = n_phi;
+    for (int lev = 0; lev < BHR_NUM_MIPS; ++lev) { ctx->level_off[lev] = off; off += (unsigned)(h * w); h /= 2; w /= 2; }
+    ctx->level_off[BHR_NUM_MIPS] = off;
+    BHR_CUDA(ctx, cudaMalloc(&ctx->mips, (size_t)off * sizeof(float4)));
+    BHR_CUDA(ctx, cudaMemsetAsync(ctx->mips, 0, (size_t)off * sizeof(float4), ctx->stream));
+    return BHR_OK;
+}
+
+extern "C" int bhr_upload_disk_texture(bhr_ctx* ctx, const float* rgba, int n_r, int n_phi) {
+    if (!ctx || !rgba) return BHR_ERR_INVALID;
+    int rc = ensure_disk_storage(ctx, n_r, n_phi);
+    if (rc) return rc;
+    BHR_CUDA(ctx, cudaMemcpyAsync(ctx->mips, rgba, (size_t)n_r * n_phi * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    rc = bhr_launch_build_mips(ctx, 1);
+    if (rc) return rc;
+    BHR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return BHR_OK;
+}
+
+extern "C" int bhr_init_background(bhr_ctx* ctx, int n_r, int n_phi, int az_freq, float az_shear, const float* edge,
+                                   const float* omega_rows) {
+    if (!ctx || !edge || !omega_rows) return BHR_ERR_INVALID;
+    int rc = ensure_disk_storage(ctx, n_r, n_phi);
+    if (rc) return rc;
+    const size_t plane = (size_t)n_r * n_phi;
+    if (!ctx->comp) {
+        BHR_CUDA(ctx, cudaMalloc(&ctx->comp, plane * BHR_N_COMP * sizeof(float)));
+        BHR_CUDA(ctx, cudaMalloc(&ctx->edge, n_r * sizeof(float)));
+        BHR_CUDA(ctx, cudaMalloc(&ctx->omega_rows, n_r * sizeof(float)));
+        BHR_CUDA(ctx, cudaMalloc(&ctx->row_stats, 2 * n_r * sizeof(float)));
+    }
+    BHR_CUDA(ctx, cudaMemsetAsync(ctx->comp, 0, plane * BHR_N_COMP * sizeof(float), ctx->stream));
+    BHR_CUDA(ctx, cudaMemcpyAsync(ctx->edge, edge, n_r * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    BHR_CUDA(ctx, cudaMemcpyAsync(ctx->omega_rows, omega_rows, n_r * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    BHR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->az_freq = az_freq; ctx->az_shear = az_shear;
+    ctx->bg_ready = 1;
+    return BHR_OK;
+}
+
+extern "C" int bhr_generate_background(bhr_ctx* ctx, float t) {
+    if (!ctx) return BHR_ERR_INVALID;
+    if (!ctx->bg_ready) BHR_FAIL(ctx, BHR_ERR_STATE, "Must call init_background_layer() first");
+    const size_t plane = (size_t)ctx->n_r * ctx->n_phi;
+    background_kernel<<<(unsigned)((plane + 255) / 256), 256, 0, ctx->stream>>>(
+        ctx->comp, ctx->n_r, ctx->n_phi, ctx->az_freq, ctx->az_shear, ctx->cfg.r_disk_inner, ctx->cfg.r_disk_outer, t);
+    BHR_CUDA(ctx, cudaGetLastError());
+    return BHR_OK;
+}
+
+extern "C" int bhr_accumulate_entities(bhr_ctx* ctx, const bhr_entity* entities, int n) {
+    if (!ctx || (n > 0 && !entities)) return BHR_ERR_INVALID;
+    if (!ctx->bg_ready) BHR_FAIL(ctx, BHR_ERR_STATE, "Must call init_background_layer() first");
+    if (n > ctx->entities_cap) {
+        if (ctx->d_entities) cudaFree(ctx->d_entities);
+        ctx->entities_cap = n + 256;
+        BHR_CUDA(ctx, cudaMalloc(&ctx->d_entities, (size_t)ctx->entities_cap * sizeof(bhr_entity)));
+    }
+    if (n > 0) {
+        BHR_CUDA(ctx, cudaMemcpyAsync(ctx->d_entities, entities, (size_t)n * sizeof(bhr_entity), cudaMemcpyHostToDevice, ctx->stream));
+        // the host array may be reused by the caller as soon as we return
+        BHR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    const size_t plane = (size_t)ctx->n_r * ctx->n_phi;
+    entity_accumulate_kernel<<<(unsigned)((plane + 255) / 256), 256, 0, ctx->stream>>>(
+        ctx->comp, ctx->n_r, ctx->n_phi, ctx->d_entities, n, ctx->omega_rows);
+    BHR_CUDA(ctx, cudaGetLastError());
+    return BHR_OK;
+}
+
+extern "C" int bhr_set_stats(bhr_ctx* ctx, float density_p98, float struct_scale, const float* row_stats) {
+    if (!ctx || !row_stats) return BHR_ERR_INVALID;
+    if (!ctx->bg_ready) BHR_FAIL(ctx, BHR_ERR_STATE, "Must call init_background_layer() first");
+    ctx->stats[0] = density_p98; ctx->stats[1] = struct_scale;
+    BHR_CUDA(ctx, cudaMemcpyAsync(ctx->row_stats, row_stats, 2 * ctx->n_r * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    BHR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return BHR_OK;
+}
+
+extern "C" int bhr_upload_comp(bhr_ctx* ctx, const float* comp) {
+    if (!ctx || !comp) return BHR_ERR_INVALID;
+    if (!ctx->bg_ready) BHR_FAIL(ctx, BHR_ERR_STATE, "Must call init_background_layer() first");
+    const size_t bytes = (size_t)ctx->n_r * ctx->n_phi * BHR_N_COMP * sizeof(float);
+    BHR_CUDA(ctx, cudaMemcpyAsync(ctx->comp, comp, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    BHR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return BHR_OK;
+}
+
+extern "C" int bhr_compose_texture(bhr_ctx* ctx, float t_offset, int enable_rt, float color_temp) {
+    if (!ctx) return BHR_ERR_INVALID;
+    if (!ctx->bg_ready) BHR_FAIL(ctx, BHR_ERR_STATE, "Must call init_background_layer() first");
+    const size_t plane = (size_t)ctx->n_r * ctx->n_phi;
+    compose_kernel<<<(unsigned)((plane + 255) / 256), 256, 0, ctx->stream>>>(
+        ctx->comp, ctx->omega_rows, ctx->edge, ctx->stats[0], ctx->stats[1], ctx->row_stats, ctx->n_r, ctx->n_phi,
+        t_offset, enable_rt, color_temp, ctx->mips);
+    BHR_CUDA(ctx, cudaGetLastError());
+    return bhr_launch_build_mips(ctx, 0);
+}
+
+extern "C" int bhr_eval_noise(bhr_ctx* ctx, const float* coords, int n, int mode, int octaves, float persistence,
+                              float lacunarity, float* out) {
+    if (!ctx || !coords || !out || n < 0) return BHR_ERR_INVALID;
+    if (n == 0) return BHR_OK;
+    float *dc = nullptr, *dout = nullptr;
+    BHR_CUDA(ctx, cudaMalloc(&dc, (size_t)n * 3 * sizeof(float)));
+    BHR_CUDA(ctx, cudaMalloc(&dout, (size_t)n * sizeof(float)));
+    BHR_CUDA(ctx, cudaMemcpyAsync(dc, coords, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    noise_eval_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(dc, n, mode, octaves, persistence, lacunarity, dout);
+    BHR_CUDA(ctx, cudaGetLastError());
+    BHR_CUDA(ctx, cudaMemcpyAsync(out, dout, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    BHR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(dc); cudaFree(dout);
+    return BHR_OK;
+}

@@ -1,0 +1,357 @@
+"""`Renderer`: the TaichiRenderer-shaped front end of libbhr.so.
+
+Same constructor arguments, methods, attributes and error behaviour as the reference's
+`TaichiRenderer` (render.py:2189-4028) for the render path, so callers (`render_image`,
+`render_video`, the reference's kernel-level unit tests) can switch classes.  Every method is a
+thin wrapper over one C-ABI call (include/bhr.h); all arithmetic runs in the sm_100a kernels.
+There is no CPU path: construction fails without a CUDA device.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _lib as L
+from .camera import build_camera
+
+R_DISK_INNER_DEFAULT = 2.0
+R_DISK_OUTER_DEFAULT = 15.0
+DISK_COLOR_TEMPERATURE = 6000
+NUM_MIP_LEVELS = 5
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _fp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+class _Field:
+    """Read-only stand-in for a Taichi field: `.to_numpy()` returns the reference's layout."""
+
+    def __init__(self, getter):
+        self._getter = getter
+
+    def to_numpy(self):
+        return self._getter()
+
+
+def compute_edge_alpha(height, inner_soft=0.1, outer_soft=0.3):
+    """Soft radial edges of the disk alpha (reference: compute_edge_alpha, render.py:437-445):
+    cubic ramp over the inner 10 % of rows, quadratic fall-off over the outer 30 %."""
+    v = np.linspace(0, 1, height).astype(np.float32)
+    alpha = np.ones_like(v)
+    lo = v < inner_soft
+    hi = v > (1 - outer_soft)
+    alpha[lo] = (v[lo] / inner_soft) ** 3.0
+    alpha[hi] = ((1 - v[hi]) / outer_soft) ** 2
+    return alpha
+
+
+class Renderer:
+    def __init__(self, width, height, skybox, disk_tex, step_size=0.1, r_max=10.0, device="gpu",
+                 r_disk_inner=R_DISK_INNER_DEFAULT, r_disk_outer=R_DISK_OUTER_DEFAULT,
+                 disk_tilt=0.0, lens_flare=False, anti_alias="disabled", aa_strength=1.0,
+                 disk_rotation_speed=0.1, ignore_taichi_cache=False, cuda_device=None):
+        # `device` ("cpu"/"gpu") and `ignore_taichi_cache` are accepted for drop-in compatibility;
+        # the kernels always run on the CUDA device `cuda_device` (default: LOCAL_RANK or 0).
+        self.width = int(width)
+        self.height = int(height)
+        self.step_size = step_size
+        self.r_max = r_max
+        self.r_disk_inner = r_disk_inner
+        self.r_disk_outer = r_disk_outer
+        self.disk_tilt = disk_tilt
+        self.anti_alias = anti_alias
+        self.aa_strength = aa_strength
+        self.disk_rotation_speed = disk_rotation_speed
+        self.num_mip_levels = NUM_MIP_LEVELS
+        if cuda_device is None:
+            cuda_device = int(os.environ.get("LOCAL_RANK", "0"))
+        self.cuda_device = cuda_device
+
+        skybox = _f32(skybox)
+        disk_tex = _f32(disk_tex)
+        self.tex_h, self.tex_w = skybox.shape[:2]
+        self.dtex_h, self.dtex_w = disk_tex.shape[:2]
+
+        self._lib = L.load()
+        cfg = L.BhrConfig(self.width, self.height, step_size, r_max, r_disk_inner, r_disk_outer,
+                          disk_tilt, int(bool(lens_flare)), 0 if anti_alias == "disabled" else 1,
+                          aa_strength, disk_rotation_speed, cuda_device)
+        ctx = C.c_void_p()
+        rc = self._lib.bhr_create(C.byref(cfg), C.byref(ctx))
+        if rc != 0:
+            raise L.BhrError(f"bhr_create failed ({rc}): {self._lib.bhr_last_error(None).decode()}")
+        self._ctx = ctx
+        self._lens_flare = bool(lens_flare)
+        self._check(self._lib.bhr_upload_skybox(ctx, _fp(skybox), self.tex_h, self.tex_w))
+        self._check(self._lib.bhr_upload_disk_texture(ctx, _fp(disk_tex), self.dtex_h, self.dtex_w))
+        self._bg_ready = False
+        self._last_flags = 0
+
+        W, H = self.width, self.height
+        self.image_field = _Field(lambda: self._planar(L.BUF_BG).transpose(2, 1, 0).copy())
+        self.disk_layer_field = _Field(lambda: self._planar(L.BUF_DISK).transpose(2, 1, 0).copy())
+        self.blur_field = _Field(lambda: self._planar(L.BUF_BLUR).transpose(2, 1, 0).copy())
+        self.final_field = _Field(lambda: self._download(L.BUF_FINAL, (H, W, 3), np.float32)
+                                  .transpose(1, 0, 2).copy())
+        self.disk_texture_field = _Field(
+            lambda: self._download(L.BUF_DISK_TEX, (self.dtex_h, self.dtex_w, 4), np.float32))
+        self.disk_mips_field = _Field(self._padded_mips)
+
+    # ------------------------------------------------------------------ plumbing
+    def _check(self, rc):
+        L.check(self._ctx, rc)
+
+    def __del__(self):
+        ctx = getattr(self, "_ctx", None)
+        if ctx:
+            self._lib.bhr_destroy(ctx)
+            self._ctx = None
+
+    def close(self):
+        self.__del__()
+
+    @property
+    def lens_flare(self):
+        return self._lens_flare
+
+    @lens_flare.setter
+    def lens_flare(self, value):
+        self._lens_flare = bool(value)
+        self._check(self._lib.bhr_set_lens_flare(self._ctx, int(self._lens_flare)))
+
+    def set_stream(self, cuda_stream):
+        """Run all kernels on the given CUDA stream handle (e.g. torch's current stream)."""
+        self._check(self._lib.bhr_set_stream(self._ctx, C.c_void_p(cuda_stream)))
+
+    def synchronize(self):
+        self._check(self._lib.bhr_synchronize(self._ctx))
+
+    def set_option(self, key, value):
+        self._check(self._lib.bhr_set_option(self._ctx, key.encode(), float(value)))
+
+    def device_buffer(self, buf_id):
+        """(device pointer, bytes) of one of the context's buffers (see bhr_buffer_id)."""
+        p, n = C.c_void_p(), C.c_size_t()
+        self._check(self._lib.bhr_buffer(self._ctx, buf_id, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def _download(self, buf_id, shape, dtype):
+        out = np.empty(shape, dtype=dtype)
+        self._check(self._lib.bhr_download(self._ctx, buf_id, out.ctypes.data, out.nbytes))
+        return out
+
+    def _planar(self, buf_id):
+        return self._download(buf_id, (3, self.height, self.width), np.float32)
+
+    def _padded_mips(self):
+        """Mip pyramid in the reference's padded layout (levels, n_r, n_phi, 4)."""
+        n_r, n_phi = self.dtex_h, self.dtex_w
+        total = sum((n_r >> l) * (n_phi >> l) for l in range(NUM_MIP_LEVELS))
+        flat = self._download(L.BUF_DISK_MIPS, (total, 4), np.float32)
+        out = np.zeros((NUM_MIP_LEVELS, n_r, n_phi, 4), dtype=np.float32)
+        off = 0
+        for l in range(NUM_MIP_LEVELS):
+            h, w = n_r >> l, n_phi >> l
+            out[l, :h, :w] = flat[off:off + h * w].reshape(h, w, 4)
+            off += h * w
+        return out
+
+    # ------------------------------------------------------------------ textures
+    def update_disk_texture(self, new_disk_tex):
+        """Replace the disk texture and rebuild its mip pyramid (render.py:2292-2312)."""
+        new_disk_tex = _f32(new_disk_tex)
+        dtex_h, dtex_w = new_disk_tex.shape[:2]
+        assert dtex_h == self.dtex_h and dtex_w == self.dtex_w, \
+            f"Texture size mismatch: expected {self.dtex_h}x{self.dtex_w}, got {dtex_h}x{dtex_w}"
+        self._check(self._lib.bhr_upload_disk_texture(self._ctx, _fp(new_disk_tex), dtex_h, dtex_w))
+
+    # ------------------------------------------------------------------ hot path
+    def _camera(self, cam_pos, fov, frame):
+        pos, right, up, forward, pw, ph = build_camera(
+            np.array(cam_pos, dtype=np.float64), fov, self.width, self.height)
+        r_escape = max(self.r_max, float(np.linalg.norm(pos)) * 2)
+        cam = L.BhrCamera()
+        for k in range(3):
+            cam.pos[k] = np.float32(pos[k])
+            cam.right[k] = np.float32(right[k])
+            cam.up[k] = np.float32(up[k])
+            cam.forward[k] = np.float32(forward[k])
+        cam.pixel_w, cam.pixel_h, cam.r_escape = float(pw), float(ph), float(r_escape)
+        cam.t_offset = float(frame) * self.disk_rotation_speed
+        return cam
+
+    def _flags(self, skip_differentials, skip_bloom, aux=False):
+        return ((L.BHR_SKIP_DIFFERENTIALS if skip_differentials else 0)
+                | (L.BHR_SKIP_BLOOM if skip_bloom else 0) | (L.BHR_WANT_AUX if aux else 0))
+
+    def render(self, cam_pos, fov, frame=0, skip_differentials=False, skip_bloom=False, out=None,
+               aux=False):
+        """Render one frame; returns (height, width, 3) float32 in [0, 1] (render.py:3865-3923).
+
+        `out` (extension): a C-contiguous (H, W, 3) float32 array to fill instead of allocating;
+        pass pinned memory (`pinned_frame()`) to avoid the driver's staging copy.
+        """
+        cam = self._camera(cam_pos, fov, frame)
+        if out is None:
+            out = np.empty((self.height, self.width, 3), dtype=np.float32)
+        assert out.dtype == np.float32 and out.flags.c_contiguous \
+            and out.shape == (self.height, self.width, 3)
+        self._check(self._lib.bhr_render(self._ctx, C.byref(cam),
+                                         self._flags(skip_differentials, skip_bloom, aux),
+                                         out.ctypes.data, None))
+        return out
+
+    def render_u8(self, cam_pos, fov, frame=0, skip_differentials=False, skip_bloom=False, out=None):
+        """As `render` but returns the 8-bit frame the drivers save: trunc(clip(img)*255)."""
+        cam = self._camera(cam_pos, fov, frame)
+        if out is None:
+            out = np.empty((self.height, self.width, 3), dtype=np.uint8)
+        assert out.dtype == np.uint8 and out.flags.c_contiguous
+        self._check(self._lib.bhr_render(self._ctx, C.byref(cam),
+                                         self._flags(skip_differentials, skip_bloom), None,
+                                         out.ctypes.data))
+        return out
+
+    def render_device(self, cam_pos, fov, frame=0, skip_differentials=False, skip_bloom=False,
+                      aux=False):
+        """Enqueue one frame and leave the results in device buffers (no host copy, no sync)."""
+        cam = self._camera(cam_pos, fov, frame)
+        self._check(self._lib.bhr_render(self._ctx, C.byref(cam),
+                                         self._flags(skip_differentials, skip_bloom, aux), None, None))
+
+    def pinned_frame(self, dtype=np.float32):
+        """A page-locked (H, W, 3) array for `render(..., out=)` / `render_u8(..., out=)`."""
+        n = self.height * self.width * 3 * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        if self._lib.bhr_host_alloc(n, C.byref(p)) != 0:
+            raise L.BhrError("bhr_host_alloc failed")
+        buf = (C.c_char * n).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=dtype).reshape(self.height, self.width, 3)
+        self.__dict__.setdefault("_pinned", []).append(p)
+        return arr
+
+    def last_aux(self):
+        """(class map u8 (H, W), RK4 evaluation counts i32 (H, W)) of the last render(aux=True)."""
+        return (self._download(L.BUF_CLASS, (self.height, self.width), np.uint8),
+                self._download(L.BUF_STEPS, (self.height, self.width), np.int32))
+
+    def last_total_steps(self):
+        v = C.c_uint64()
+        self._check(self._lib.bhr_last_total_steps(self._ctx, C.byref(v)))
+        return v.value
+
+    def last_stage_ms(self):
+        arr = (C.c_float * 5)()
+        self._check(self._lib.bhr_last_stage_ms(self._ctx, arr))
+        return dict(zip(("ray_march", "bloom_h", "bloom_v_composite", "gap", "total"), list(arr)))
+
+    # ------------------------------------------------------------------ disk-texture pipeline
+    def init_background_layer(self, n_r, n_phi, seed=42):
+        """Allocate the 13-plane component field and draw the azimuthal-hotspot parameters
+        (render.py:3491-3547; the two draws from default_rng(seed) keep their order)."""
+        rng = np.random.default_rng(seed)
+        self._bg_az_freq = int(rng.integers(2, 5))
+        self._bg_az_shear = float(rng.uniform(2.0, 4.0))
+        edge = compute_edge_alpha(n_r).astype(np.float32)
+        r_norm = np.linspace(0, 1, n_r)
+        r_vals = self.r_disk_inner + (self.r_disk_outer - self.r_disk_inner) * r_norm
+        omega_rows = np.sqrt(0.5 / (r_vals ** 3 + 1e-6)).astype(np.float32)
+        self._bg_omega_all_np = omega_rows
+        self._bg_r_norm_all = r_norm
+        self._bg_edge_np = edge
+        self._bg_n_r, self._bg_n_phi = n_r, n_phi
+        self._check(self._lib.bhr_init_background(self._ctx, n_r, n_phi, self._bg_az_freq,
+                                                  self._bg_az_shear, _fp(edge), _fp(omega_rows)))
+        # initial, deliberately loose stats (render.py:3532-3542)
+        tb_init = np.clip(1.0 - np.linspace(0, 1, n_r), 0, 1) ** 1.3 * 0.25
+        self._stats = np.array([0.5, 0.5], dtype=np.float32)
+        self._row_stats = np.column_stack([np.maximum(tb_init, 0.25).astype(np.float32),
+                                           np.maximum(tb_init * 0.8, 0.10).astype(np.float32)])
+        self._push_stats()
+        self._param_enable_rt = 1
+        self._param_color_temp = float(DISK_COLOR_TEMPERATURE)
+        self._bg_ready = True
+        self._comp_field = _Field(lambda: self._download(L.BUF_COMP, (13, n_r, n_phi), np.float32))
+        self._edge_field = _Field(lambda: self._bg_edge_np.copy())
+        self._omega_rows_field = _Field(lambda: self._bg_omega_all_np.copy())
+        self._param_stats_field = _Field(lambda: self._stats.copy())
+        self._param_row_stats_field = _Field(lambda: self._row_stats.copy())
+
+    def _push_stats(self):
+        rows = _f32(self._row_stats)
+        self._check(self._lib.bhr_set_stats(self._ctx, float(self._stats[0]), float(self._stats[1]),
+                                            _fp(rows)))
+
+    def generate_background(self, t):
+        """Time-evolved simplex-FBM background planes [0,1,2,3,4,11,12] (render.py:3549-3562)."""
+        assert self._bg_ready, "Must call init_background_layer() first"
+        self._check(self._lib.bhr_generate_background(self._ctx, float(t)))
+
+    def accumulate_entity_layer(self, factories, now):
+        """Sum every alive entity into comp[5:11] on the device (render.py:3564-3653)."""
+        from .lifecycle import pack_entities
+        assert self._bg_ready, "Must call init_background_layer() first"
+        ents = pack_entities(factories, now, self._bg_n_r)
+        arr = (L.BhrEntity * max(len(ents), 1))(*ents)
+        self._check(self._lib.bhr_accumulate_entities(self._ctx, arr, len(ents)))
+
+    def recompute_interactive_stats(self):
+        """Normalisation statistics from the current component field (render.py:3655-3712):
+        98th percentile of the density mix, 95th percentile of the positive structure
+        temperature, per-row max / 70 % quantile of the scaled structure temperature."""
+        comp = self._comp_field.to_numpy()
+        edge = self._bg_edge_np
+        rt_w = 0.20 if self._param_enable_rt else 0.0
+        dm = comp[12]
+        density = (0.15 + 0.10 * comp[1] + 0.30 * comp[3] + 0.20 * comp[9] + 0.30 * comp[5]
+                   + rt_w * comp[7]) * dm
+        density *= edge[:, None]
+        p98 = max(float(np.percentile(density, 98)), 0.01)
+        struct = (comp[2] + comp[4] + comp[6] + comp[8] + comp[10]) * dm
+        positive = struct > 0
+        scale = float(np.percentile(struct[positive], 95)) if np.any(positive) else 1.0
+        scale = max(scale, 0.01)
+        scaled = np.clip(struct / (scale + 1e-6) * 0.8, 0, 1.2)
+        row_max = np.max(scaled, axis=1).astype(np.float32)
+        row_p70 = np.quantile(scaled, 0.7, axis=1).astype(np.float32)
+        tb_max = np.max(comp[0], axis=1).astype(np.float32)
+        row_max = np.maximum(row_max, tb_max)
+        row_p70 = np.maximum(row_p70, tb_max * 0.8)
+        self._stats = np.array([p98, scale], dtype=np.float32)
+        self._row_stats = np.column_stack([row_max, row_p70]).astype(np.float32)
+        self._push_stats()
+
+    _SOLO_PAIRS = {0: [], 1: [2], 2: [1], 3: [4], 4: [3], 5: [6], 6: [5], 7: [8], 8: [7],
+                   9: [10], 10: [9], 11: [], 12: []}
+
+    def compose_interactive_texture(self, solo_idx=-1):
+        """Compose the RGBA disk texture from the component field and rebuild the mips
+        (render.py:3714-3767).  solo_idx >= 0 isolates one component (debug aid)."""
+        if solo_idx >= 0:
+            comp = self._comp_field.to_numpy()
+            keep = {solo_idx} | set(self._SOLO_PAIRS.get(solo_idx, []))
+            for i in range(13):
+                if i not in keep:
+                    comp[i] = 1.0 if i == 12 else 0.0
+            self._check(self._lib.bhr_upload_comp(self._ctx, _fp(_f32(comp))))
+            self.recompute_interactive_stats()
+        self._check(self._lib.bhr_compose_texture(self._ctx, 0.0, int(self._param_enable_rt),
+                                                  float(self._param_color_temp)))
+
+    def eval_noise(self, coords, mode="simplex", octaves=4, persistence=0.5, lacunarity=2.0):
+        """Evaluate the device simplex / FBM noise at (N, 3) points (render.py:3769-3790)."""
+        coords = _f32(coords)
+        out = np.empty(coords.shape[0], dtype=np.float32)
+        self._check(self._lib.bhr_eval_noise(self._ctx, _fp(coords), coords.shape[0],
+                                             0 if mode == "simplex" else 1, int(octaves),
+                                             float(persistence), float(lacunarity), _fp(out)))
+        return out
+
+
+# drop-in alias: code written against the reference can keep the class name
+TaichiRenderer = Renderer

@@ -87,6 +87,12 @@ int bhr_set_stream(bhr_ctx* ctx, void* cuda_stream); /* NULL = the context's own
 int bhr_synchronize(bhr_ctx* ctx);
 int bhr_set_lens_flare(bhr_ctx* ctx, int enabled);  /* renderer.lens_flare attribute */
 int bhr_version(void);
+/* tuning knobs for tests / benchmarks: "raymarch_mode" = 0 scalar FFMA, 1 packed FFMA2 (default),
+ * 2 strict (reference operation order, exactly rounded; slow, for parity triage) */
+int bhr_set_option(bhr_ctx* ctx, const char* key, double value);
+/* pinned host memory so that frame read-back DMA needs no staging copy */
+int bhr_host_alloc(size_t bytes, void** out);
+int bhr_host_free(void* p);
 
 /* texture_field.from_numpy (render.py:2232-2233): skybox (h, w, 3) f32 host */
 int bhr_upload_skybox(bhr_ctx* ctx, const float* rgb, int h, int w);
