@@ -61,6 +61,7 @@ SIGNATURES = {
     "bhr_buffer": (C.c_int, [_P, C.c_int, C.POINTER(_P), C.POINTER(C.c_size_t)]),
     "bhr_download": (C.c_int, [_P, C.c_int, _P, C.c_size_t]),
     "bhr_last_total_steps": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
+    "bhr_last_retrace_count": (C.c_int, [_P, C.POINTER(C.c_uint32)]),
     "bhr_last_stage_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "bhr_init_background": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_float, _FP, _FP]),
     "bhr_generate_background": (C.c_int, [_P, C.c_float]),

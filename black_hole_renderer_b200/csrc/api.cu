@@ -60,6 +60,12 @@ extern "C" int bhr_create(const bhr_config* cfg, bhr_ctx** out) {
     CREATE_CHECK(cudaMalloc(&ctx->steps, plane * sizeof(int)));
     CREATE_CHECK(cudaMalloc(&ctx->d_total_steps, sizeof(unsigned long long)));
     CREATE_CHECK(cudaMalloc(&ctx->d_flare_sums, 3 * sizeof(double)));
+    CREATE_CHECK(cudaMalloc(&ctx->retrace_queue, plane * sizeof(unsigned long long)));
+    CREATE_CHECK(cudaMemset(ctx->retrace_queue, 0, plane * sizeof(unsigned long long)));
+    CREATE_CHECK(cudaMalloc(&ctx->d_queue_count, 4 * sizeof(unsigned int)));
+    CREATE_CHECK(cudaMemset(ctx->d_queue_count, 0, 4 * sizeof(unsigned int)));
+    ctx->retrace_min_cross = 3;
+    ctx->retrace_band = 0.02f;
     CREATE_CHECK(cudaMemset(ctx->bg, 0, plane * 3 * sizeof(float)));
     CREATE_CHECK(cudaMemset(ctx->disk, 0, plane * 3 * sizeof(float)));
     CREATE_CHECK(cudaMemset(ctx->hblur, 0, plane * 3 * sizeof(float)));
@@ -84,7 +90,7 @@ extern "C" void bhr_destroy(bhr_ctx* ctx) {
     cudaSetDevice(ctx->cfg.device);
     if (ctx->own_stream) { cudaStreamSynchronize(ctx->own_stream); }
     void* ptrs[] = {ctx->sky, ctx->mips, ctx->tex_staging, ctx->bg, ctx->disk, ctx->hblur, ctx->blur, ctx->final_f32,
-                    ctx->final_u8, ctx->cls, ctx->steps, ctx->d_total_steps, ctx->d_flare_sums, ctx->d_wtab, ctx->d_wsum_x,
+                    ctx->final_u8, ctx->cls, ctx->steps, ctx->d_total_steps, ctx->d_flare_sums, ctx->retrace_queue, ctx->d_queue_count, ctx->d_wtab, ctx->d_wsum_x,
                     ctx->d_wsum_y, ctx->comp, ctx->edge, ctx->omega_rows, ctx->row_stats, ctx->d_entities};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int k = 0; k < 6; ++k) if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
@@ -115,6 +121,8 @@ extern "C" int bhr_set_lens_flare(bhr_ctx* ctx, int enabled) {
 extern "C" int bhr_set_option(bhr_ctx* ctx, const char* key, double value) {
     if (!key) return BHR_ERR_INVALID;
     if (!strcmp(key, "raymarch_mode")) { bhr_raymarch_mode_override = (int)value; return BHR_OK; }
+    if (ctx && !strcmp(key, "retrace_min_cross")) { ctx->retrace_min_cross = (int)value; return BHR_OK; }
+    if (ctx && !strcmp(key, "retrace_band")) { ctx->retrace_band = (float)value; return BHR_OK; }
     if (ctx) snprintf(ctx->err, sizeof(ctx->err), "unknown option %s", key);
     return BHR_ERR_INVALID;
 }
@@ -227,6 +235,15 @@ extern "C" int bhr_last_total_steps(bhr_ctx* ctx, uint64_t* out) {
     BHR_CUDA(ctx, cudaMemcpyAsync(&v, ctx->d_total_steps, sizeof(v), cudaMemcpyDeviceToHost, ctx->stream));
     BHR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     *out = v;
+    return BHR_OK;
+}
+
+extern "C" int bhr_last_retrace_count(bhr_ctx* ctx, uint32_t* out) {
+    if (!ctx || !out) return BHR_ERR_INVALID;
+    unsigned int v[2] = {0, 0};
+    BHR_CUDA(ctx, cudaMemcpyAsync(v, ctx->d_queue_count, sizeof(v), cudaMemcpyDeviceToHost, ctx->stream));
+    BHR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = v[0];
     return BHR_OK;
 }
 

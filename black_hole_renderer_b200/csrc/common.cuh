@@ -35,6 +35,12 @@ struct RayParams {
     uint8_t* cls;               // (H, W) or nullptr
     int* steps;                 // (H, W) or nullptr
     unsigned long long* total_steps; // or nullptr
+    unsigned long long* queue;  // (serial << 32 | pixel) entries to re-trace in strict mode, or nullptr
+    unsigned int* queue_count;  // tail: entries appended so far
+    unsigned int queue_serial;  // tags the entries of this launch
+    int retrace_min_cross;
+    float retrace_band;         // |b / b_crit - 1| below which a ray is traced by the strict integrator
+    float inv_rcam3;            // 1 / |cam|^3
 };
 
 struct bhr_ctx {
@@ -52,6 +58,7 @@ struct bhr_ctx {
     uint8_t* final_u8;                 // (H, W, 3)
     uint8_t* cls; int* steps;
     unsigned long long* d_total_steps;
+    unsigned long long* retrace_queue; unsigned int* d_queue_count; int retrace_min_cross; unsigned int queue_serial; float retrace_band;
     double* d_flare_sums;              // {sum B, sum x*B, sum y*B}
 
     int bloom_R; float sigma_scale;

@@ -1,0 +1,216 @@
+"""Drivers above the renderer: single frame, orbit/static video with resume, frame sharding.
+
+Reference: render_image (render.py:4031-4076), render_video (4356-4511), save_image (420-425),
+compute_disk_texture_resolution (1128-1149), load_disk_texture (448-459).  Video frames are
+independent given the lifecycle state, so with several GPUs (one process per GPU, torchrun) the
+frames are dealt to ranks in blocks of 60 -- the cadence at which the normalisation statistics
+are recomputed (render.py:4457) -- with no data-path collective.
+"""
+import hashlib
+import json
+import math
+import os
+import shutil
+import time
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+from PIL import Image
+
+from .lifecycle import advance_lifecycle_frame, init_lifecycle_system
+from .renderer import R_DISK_INNER_DEFAULT, R_DISK_OUTER_DEFAULT, Renderer, compute_edge_alpha
+from .skybox import load_or_generate_skybox
+
+STATS_PERIOD = 60   # frames between recompute_interactive_stats calls
+
+
+def save_image(image, path):
+    """PNG of trunc(clip(image, 0, 1) * 255) (render.py:420-425)."""
+    os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
+    Image.fromarray((np.clip(image, 0, 1) * 255).astype(np.uint8), "RGB").save(path)
+    print(f"Saved: {path}")
+
+
+def compute_disk_texture_resolution(width, height, cam_pos, fov, r_inner, r_outer, rs=1.0):
+    """(n_phi, n_r): about one azimuthal texel per pixel across the disk's angular extent and
+    half a radial texel per pixel, floored at 256 x 128 and rounded up to multiples of 16."""
+    distance = math.sqrt(cam_pos[0] ** 2 + cam_pos[1] ** 2 + cam_pos[2] ** 2)
+    half_angle = math.atan(r_outer / distance)
+    fov_rad = fov * math.pi / 180.0
+    n_phi = max(256, int(width * (2 * half_angle / fov_rad)))
+    n_r = max(128, int(height * (half_angle / fov_rad) * 0.5))
+    return n_phi + (16 - n_phi % 16) % 16, n_r + (16 - n_r % 16) % 16
+
+
+def load_disk_texture(path):
+    """RGB image -> (h, w, 4) float32 with the soft-edge alpha, or None when no file is given."""
+    if path and os.path.isfile(path):
+        print(f"Loading disk texture: {path}")
+        rgb = np.array(Image.open(path).convert("RGB"), dtype=np.float32) / 255.0
+        h, w = rgb.shape[:2]
+        alpha = np.broadcast_to(compute_edge_alpha(h)[:, None, None].astype(np.float32), (h, w, 1))
+        return np.concatenate([rgb, alpha], axis=2)
+    return None
+
+
+def make_renderer(width, height, cam_pos, fov, skybox_path=None, n_stars=6000, tex_w=2048,
+                  tex_h=1024, disk_texture_path=None, **renderer_kw):
+    """Skybox + (placeholder | loaded) disk texture + Renderer; returns (renderer, use_lifecycle)."""
+    skybox, _, _ = load_or_generate_skybox(skybox_path, tex_w, tex_h, n_stars)
+    disk_tex = load_disk_texture(disk_texture_path)
+    use_lifecycle = disk_tex is None
+    if use_lifecycle:
+        n_phi, n_r = compute_disk_texture_resolution(
+            width, height, cam_pos, fov, renderer_kw.get("r_disk_inner", R_DISK_INNER_DEFAULT),
+            renderer_kw.get("r_disk_outer", R_DISK_OUTER_DEFAULT))
+        disk_tex = np.zeros((n_r, n_phi, 4), dtype=np.float32)
+    return Renderer(width, height, skybox, disk_tex, **renderer_kw), use_lifecycle
+
+
+def render_image(width, height, cam_pos, fov, step_size, skybox_path=None, n_stars=6000,
+                 tex_w=2048, tex_h=1024, r_max=10.0, device="gpu", disk_texture_path=None,
+                 r_disk_inner=R_DISK_INNER_DEFAULT, r_disk_outer=R_DISK_OUTER_DEFAULT, disk_tilt=0.0,
+                 lens_flare=False, anti_alias="disabled", aa_strength=1.0, disk_rotation_speed=0.1,
+                 disk_generation_scale=2, force_regenerate_disk_texture=False,
+                 ignore_taichi_cache=False):
+    """One frame; the disk texture comes from the lifecycle system at t = 0 unless a file is
+    given (render.py:4031-4076).  Deprecated arguments are accepted and ignored."""
+    renderer, use_lifecycle = make_renderer(
+        width, height, cam_pos, fov, skybox_path, n_stars, tex_w, tex_h, disk_texture_path,
+        step_size=step_size, r_max=r_max, device=device, r_disk_inner=r_disk_inner,
+        r_disk_outer=r_disk_outer, disk_tilt=disk_tilt, lens_flare=lens_flare,
+        anti_alias=anti_alias, aa_strength=aa_strength, disk_rotation_speed=disk_rotation_speed)
+    if use_lifecycle:
+        factories = init_lifecycle_system(renderer, renderer.dtex_h, renderer.dtex_w, seed=42)
+        advance_lifecycle_frame(renderer, factories, t=0.0, dt=0.0, recompute_stats=True)
+    t0 = time.time()
+    print(f"B200: {width}x{height}, cam_pos={list(cam_pos)}, fov={fov}°, step_size={step_size}")
+    img = renderer.render(cam_pos, fov, frame=0)
+    print(f"Done in {time.time() - t0:.3f}s")
+    return img
+
+
+def orbit_camera(static_cam_pos, frame, n_frames, orbit_degrees):
+    """Camera of orbit frame `frame`: radius |pov| (3-D norm), height pov.z (render.py:4440-4446)."""
+    radius = float(np.linalg.norm(static_cam_pos))
+    angle = np.radians(frame * (orbit_degrees / n_frames))
+    return [radius * np.cos(angle), radius * np.sin(angle), static_cam_pos[2]]
+
+
+def frame_owner(frame, world_size, block=STATS_PERIOD):
+    """Rank that renders `frame` when frames are dealt in `block`-frame blocks round-robin."""
+    return (frame // block) % world_size
+
+
+def render_video(renderer, width, height, n_frames, fps, output_path, fov, static_cam_pos,
+                 orbit=False, resume=False, disk_rotation_speed=0.1, orbit_degrees=360.0,
+                 rank=0, world_size=1, barrier=None, **_deprecated_kwargs):
+    """Render `n_frames` frames to PNGs under .frames_<md5(output)>/ and mux them.
+
+    Same temp-dir / progress.json protocol as the reference (render.py:4380-4405, 4469-4472).
+    With world_size > 1 each rank renders the frames it owns (`frame_owner`), writes
+    progress.<rank>.json, and rank 0 merges the per-rank lists and muxes after `barrier()`.
+    """
+    out_dir = os.path.dirname(output_path)
+    os.makedirs(out_dir or ".", exist_ok=True)
+    temp_dir = os.path.join(out_dir, ".frames_" + hashlib.md5(output_path.encode()).hexdigest()[:16])
+    progress_file = os.path.join(temp_dir, "progress.json")
+    my_progress = progress_file if world_size == 1 else os.path.join(temp_dir, f"progress.{rank}.json")
+    params = {"n_frames": n_frames, "fov": fov, "orbit": orbit,
+              "disk_rotation_speed": disk_rotation_speed, "orbit_degrees": orbit_degrees}
+
+    completed = set()
+    if resume and os.path.isdir(temp_dir) and os.path.isfile(progress_file):
+        with open(progress_file) as f:
+            saved = json.load(f)
+        if saved.get("params", {}) != params:
+            print("Warning: parameters changed, starting over")
+            if rank == 0:
+                shutil.rmtree(temp_dir)
+        else:
+            completed = set(saved.get("completed", []))
+            print(f"Resuming: {len(completed)}/{n_frames} frames already rendered")
+    if barrier:
+        barrier()
+    os.makedirs(temp_dir, exist_ok=True)
+
+    pool = ThreadPoolExecutor(max_workers=int(os.environ.get("BHR_PNG_WORKERS", "2")))
+    pending = []
+
+    def save_png(path, img_u8):
+        Image.fromarray(img_u8, "RGB").save(path)
+
+    n_r, n_phi = renderer.dtex_h, renderer.dtex_w
+    factories = init_lifecycle_system(renderer, n_r, n_phi, seed=42)
+    dt = disk_rotation_speed
+    if completed:
+        # replay the simulation up to the resume point (render.py:4427-4434); only the host
+        # state and the statistics are stateful, so the device stages run at stats frames only
+        for f in range(max(completed) + 1):
+            advance_lifecycle_frame(renderer, factories, f * dt, dt)
+
+    t_start = time.time()
+    rendered = 0
+    for frame in range(n_frames):
+        t = frame * dt
+        cam_pos = orbit_camera(static_cam_pos, frame, n_frames, orbit_degrees) if orbit else static_cam_pos
+        if frame in completed:
+            continue
+        mine = frame_owner(frame, world_size) == rank
+        if not mine:
+            for f in factories.values():      # keep the RNG streams in step; no device work
+                f.tick(now=t, dt=dt)
+            continue
+        advance_lifecycle_frame(renderer, factories, t, dt, recompute_stats=(frame % STATS_PERIOD == 0))
+        img_u8 = renderer.render_u8(cam_pos, fov, frame=0)
+        rendered += 1
+        if len(pending) >= 4:
+            pending.pop(0).result()
+        pending.append(pool.submit(save_png, os.path.join(temp_dir, f"frame_{frame:04d}.png"), img_u8))
+        completed.add(frame)
+        if rendered % 10 == 0 or frame == n_frames - 1:
+            with open(my_progress, "w") as f:
+                json.dump({"params": params, "completed": sorted(completed)}, f)
+        if rendered % 100 == 0:
+            print(f"  [rank {rank}] frame {frame}/{n_frames}, {rendered / (time.time() - t_start):.1f} frames/s")
+    for f in pending:
+        f.result()
+    pool.shutdown(wait=True)
+    with open(my_progress, "w") as f:
+        json.dump({"params": params, "completed": sorted(completed)}, f)
+    if barrier:
+        barrier()
+    if rank != 0:
+        return
+    if world_size > 1:
+        for r in range(world_size):
+            p = os.path.join(temp_dir, f"progress.{r}.json")
+            if os.path.isfile(p):
+                with open(p) as f:
+                    completed |= set(json.load(f).get("completed", []))
+        with open(progress_file, "w") as f:
+            json.dump({"params": params, "completed": sorted(completed)}, f)
+    if rendered:
+        print(f"Session rendered {rendered} frames in {(time.time() - t_start) / 60:.2f} min")
+    if len(completed) < n_frames:
+        print(f"Warning: only {len(completed)}/{n_frames} frames completed. Run again to resume.")
+        return
+    mux_video(temp_dir, n_frames, fps, output_path)
+
+
+def mux_video(temp_dir, n_frames, fps, output_path):
+    """x264 mux through imageio/pyav as the reference does (render.py:4497-4503); host I/O,
+    outside the render path -- skipped with a hint when imageio is not installed."""
+    try:
+        import imageio.v3 as iio
+    except Exception:
+        print(f"imageio not available: frames kept in {temp_dir}; encode with\n"
+              f"  ffmpeg -framerate {fps} -i {temp_dir}/frame_%04d.png -c:v libx264 -crf 18 "
+              f"-pix_fmt yuv420p {output_path}")
+        return
+    writer = iio.imopen(output_path, "w", plugin="pyav")
+    writer.init_video_stream("libx264", fps=fps)
+    for frame in range(n_frames):
+        writer.write_frame(iio.imread(os.path.join(temp_dir, f"frame_{frame:04d}.png")))
+    writer.close()
+    print(f"Video saved: {output_path}")

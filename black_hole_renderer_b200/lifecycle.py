@@ -1,0 +1,385 @@
+"""Host model of the disk's transient structures (filaments, hotspots, RT spikes).
+
+Reference: EntityInstance / EntityFactory (render.py:493-792), _spawn_single_* (1667-1866),
+_init_lifecycle_system / _advance_lifecycle_frame (4079-4153).  The model is driven by three
+numpy PCG64 streams; the ORDER of the draws is the contract and is kept:
+
+  filament : source_phi, r_pos, sigma_r, sigma_phi0, peak_density, temp_ratio
+  hotspot  : phi, r_rand, phi_width, r_width_extra, intensity_extra, (unused power(0.4) draw)
+  rt_spike : phi, r_base_u, phi_width, r_length, intensity, delta_T
+  then, for every spawn: lifetime, and the four fade-noise draws (freq1, freq2, phase1, phase2)
+
+Unlike the reference, entities keep only their PARAMETERS: the per-row azimuthal profiles are
+evaluated by the device kernel (csrc/texture.cu, entity_accumulate_kernel) instead of being
+tabulated on the host and rolled with numpy every frame (0.71 s/frame at the fhd texture).  The
+tabulated arrays remain available lazily (`phi_density`, `phi_temp`, `fade_noise`) for callers
+that inspect them.
+"""
+import math
+from typing import List, Tuple
+
+import numpy as np
+
+from . import _lib as L
+
+FILAMENT_SHEAR_ALPHA = 0.1
+FILAMENT_TAU_COOL = 50.0
+FILAMENT_DEATH_THRESHOLD = 0.008
+FILAMENT_MAX_LIFETIME = 120.0
+FILAMENT_BIRTH_FADE_DUR = 5.0
+
+KIND = {"filament": 0, "hotspot": 1, "rt_spike": 2}
+TWO_PI = 2 * np.pi
+
+
+def _rows_where(mask, r_norm_all, fallback_r):
+    idx = np.flatnonzero(mask)
+    if idx.size == 0:
+        c = int(np.argmin(np.abs(r_norm_all - fallback_r)))
+        return c, c + 1
+    return int(idx[0]), int(idx[-1]) + 1
+
+
+def _nearest_omega(r_norm_all, omega_all, r):
+    return float(omega_all[int(np.argmin(np.abs(r_norm_all - r)))])
+
+
+def draw_filament(rng, r_norm_all, omega_all):
+    """Six draws; a circular Gaussian blob later sheared into an arc (render.py:1703-1722)."""
+    source_phi = float(rng.uniform(0, TWO_PI))
+    r_pos = float(rng.uniform(0.05, 0.95))
+    base_r = 0.05 + r_pos ** 0.6 * 0.9
+    sigma_r = float(rng.uniform(0.005, 0.015))
+    sigma_phi0 = float(rng.uniform(0.04, 0.10))
+    peak_density = float(rng.uniform(0.5, 1.0))
+    peak_temp = peak_density * float(rng.uniform(0.15, 0.35))
+    rows = _rows_where(np.abs(r_norm_all - base_r) < 4 * sigma_r, r_norm_all, base_r)
+    return dict(rows=rows, omega=_nearest_omega(r_norm_all, omega_all, base_r), source_phi=source_phi,
+                base_r=base_r, sigma_r=sigma_r, sigma_phi0=sigma_phi0, peak_density=peak_density,
+                peak_temp=peak_temp)
+
+
+def draw_hotspot(rng, r_norm_all, omega_all):
+    """Six draws; von-Mises x Gaussian bright patch (render.py:1754-1793)."""
+    phi0 = float(rng.uniform(0, TWO_PI))
+    r_rand = float(rng.uniform(0, 1))
+    h_r = 0.1 + r_rand ** 0.6 * 0.85
+    phi_width = float(rng.uniform(0.08, 0.20))
+    r_width = 0.02 + float(rng.uniform(0, 0.03))
+    intensity = 0.3 + (1 - h_r) * 0.6 + float(rng.uniform(0, 0.1))
+    rng.power(0.4)                                  # h_delta_T: drawn by the reference, never used
+    lo, hi = h_r - 3 * r_width, h_r + 3 * r_width
+    rows = _rows_where((r_norm_all >= lo) & (r_norm_all <= hi), r_norm_all, h_r)
+    return dict(rows=rows, omega=_nearest_omega(r_norm_all, omega_all, h_r), phi0=phi0, r0=h_r,
+                phi_width=phi_width, r_width=r_width, intensity=intensity)
+
+
+def draw_rt_spike(rng, r_norm_all, omega_all):
+    """Six draws; radial Rayleigh-Taylor finger near the inner edge (render.py:1825-1866)."""
+    phi0 = float(rng.uniform(0, TWO_PI))
+    r_base = float(np.power(rng.uniform(0.01, 0.15), 1.5))
+    phi_width = float(rng.uniform(0.08, 0.20))
+    r_length = float(rng.uniform(0.08, 0.20))
+    intensity = float(rng.uniform(0.8, 1.0))
+    delta_T = float(rng.uniform(0.5, 1.2))
+    lo, hi = max(r_base - 0.02, 0.0), r_base + r_length * 2.5
+    rows = _rows_where((r_norm_all >= lo) & (r_norm_all <= hi), r_norm_all, r_base)
+    return dict(rows=rows, omega=_nearest_omega(r_norm_all, omega_all, r_base + r_length * 0.5),
+                phi0=phi0, r0=r_base, phi_width=phi_width, r_length=r_length, intensity=intensity,
+                delta_T=delta_T)
+
+
+_DRAW = {"filament": draw_filament, "hotspot": draw_hotspot, "rt_spike": draw_rt_spike}
+
+
+def _profiles(kind, q, r_norm_all, n_phi):
+    """Tabulate (phi_density, phi_temp) like the reference's spawn functions (float32 rows)."""
+    r0, r1 = q["rows"]
+    if kind == "filament":
+        e = np.empty((0, 0), dtype=np.float32)
+        return e, e
+    phi = np.linspace(0, TWO_PI, n_phi, endpoint=False)
+    kappa = 1.5 / (q["phi_width"] ** 2)
+    phi_prof = np.exp(kappa * (np.cos(phi - q["phi0"]) - 1))
+    dens = np.zeros((r1 - r0, n_phi), dtype=np.float32)
+    temp = np.zeros((r1 - r0, n_phi), dtype=np.float32)
+    for k, ri in enumerate(range(r0, r1)):
+        d = r_norm_all[ri] - q["r0"]
+        if kind == "hotspot":
+            radial = np.exp(-0.5 * (d / (q["r_width"] + 1e-8)) ** 2)
+            dens[k] = phi_prof * radial * q["intensity"]
+            temp[k] = dens[k] * 0.12
+        else:
+            fade_out = np.clip(q["r_length"] * 2 - d, 0, 1)
+            fade_in = np.clip(d / (q["r_length"] * 0.3 + 1e-8), 0, 1)
+            radial = np.exp(-0.5 * (d / (q["r_length"] * 0.4 + 1e-8)) ** 2) * fade_out * fade_in
+            dens[k] = phi_prof * radial * q["intensity"]
+            temp[k] = dens[k] * q["delta_T"]
+    dens = np.clip(dens, 0, 1)
+    if kind == "hotspot":
+        temp = np.clip(temp, 0, 1)
+    return dens, temp
+
+
+class EntityInstance:
+    """One transient structure; same attribute / method surface as the reference's dataclass."""
+
+    def __init__(self, entity_type, q, birth_time, lifetime, fade_in, fade_out, fade_spec,
+                 r_norm_all, n_phi):
+        self.entity_type = entity_type
+        self.q = q
+        self.birth_time = birth_time
+        self.lifetime = lifetime
+        self.fade_in = fade_in
+        self.fade_out = fade_out
+        self.omega = q["omega"]
+        self._fade_spec = fade_spec
+        self._r_norm_all = r_norm_all
+        self._n_phi = n_phi
+        self._tab = None
+        self.row_indices = np.arange(q["rows"][0], q["rows"][1])
+        f = entity_type == "filament"
+        self.source_phi = q["source_phi"] if f else 0.0
+        self.total_extent = TWO_PI if f else 0.0
+        self.alpha_shear = FILAMENT_SHEAR_ALPHA * self.omega if f else 0.0
+        self.tau_cool = FILAMENT_TAU_COOL
+        self.blob_base_r = q["base_r"] if f else 0.0
+        self.blob_sigma_r = q["sigma_r"] if f else 0.0
+        self.blob_sigma_phi0 = q["sigma_phi0"] if f else 0.0
+        self.blob_peak_density = q["peak_density"] if f else 0.0
+        self.blob_peak_temp = q["peak_temp"] if f else 0.0
+
+    # lazily tabulated arrays (never needed by the device path)
+    def _tabulate(self):
+        if self._tab is None:
+            self._tab = _profiles(self.entity_type, self.q, self._r_norm_all, self._n_phi)
+        return self._tab
+
+    @property
+    def phi_density(self):
+        return self._tabulate()[0]
+
+    @property
+    def phi_temp(self):
+        return self._tabulate()[1]
+
+    @property
+    def fade_noise(self):
+        f1, f2, p1, p2 = self._fade_spec
+        phi = np.linspace(0, TWO_PI, self._n_phi, endpoint=False)
+        n = 0.6 * np.sin(phi * f1 + p1) + 0.4 * np.sin(phi * f2 + p2)
+        return np.clip(n * 0.5 + 0.5, 0, 1).astype(np.float32)
+
+    @property
+    def total_duration(self):
+        return self.fade_in + self.lifetime + self.fade_out
+
+    def density_factor(self, age):
+        """Filament shear dilution x radiative cooling: (s0 / (s0 + a*age)) * exp(-age / tau)."""
+        s0 = max(self.blob_sigma_phi0, 1e-6)
+        shear = s0 / (s0 + self.alpha_shear * age)
+        cool = math.exp(-age / self.tau_cool) if self.tau_cool > 0 else 1.0
+        return shear * cool
+
+    def is_dead(self, now):
+        age = now - self.birth_time
+        if self.entity_type == "filament":
+            if age >= FILAMENT_MAX_LIFETIME:
+                return True
+            return age >= 0 and self.density_factor(age) < FILAMENT_DEATH_THRESHOLD
+        return age >= self.total_duration
+
+    def fade_factor(self, now):
+        """Linear fade-in / plateau / fade-out envelope of hotspots and RT spikes."""
+        age = now - self.birth_time
+        if age < 0:
+            return 0.0
+        if age < self.fade_in:
+            return age / self.fade_in if self.fade_in > 0 else 1.0
+        rest = age - self.fade_in
+        if rest < self.lifetime:
+            return 1.0
+        rest -= self.lifetime
+        if rest < self.fade_out:
+            return 1.0 - rest / self.fade_out if self.fade_out > 0 else 0.0
+        return 0.0
+
+
+class EntityFactory:
+    """Keeps `target_count` entities alive: culls the dead, spawns at target/avg_lifetime per
+    second (render.py:624-792).  `spawn_fn` is accepted for signature compatibility; the draw
+    routine is selected by `entity_type`."""
+
+    def __init__(self, spawn_fn, target_count: int, lifetime_range: Tuple[float, float],
+                 fade_in: float, fade_out: float, n_r: int, n_phi: int, r_norm_all, omega_all,
+                 seed: int = 0, entity_type: str = "generic"):
+        self.spawn_fn = spawn_fn
+        self.target_count = target_count
+        self.lifetime_range = lifetime_range
+        self.fade_in = fade_in
+        self.fade_out = fade_out
+        self.n_r = n_r
+        self.n_phi = n_phi
+        self.r_norm_all = r_norm_all
+        self.omega_all = omega_all
+        self.rng = np.random.default_rng(seed)
+        self.entities: List[EntityInstance] = []
+        self._spawn_debt = 0.0
+        self.entity_type = entity_type
+        if entity_type not in _DRAW:
+            raise ValueError(f"unknown entity_type {entity_type!r}")
+
+    def _spawn_one(self, now):
+        q = _DRAW[self.entity_type](self.rng, self.r_norm_all, self.omega_all)
+        lifetime = float(self.rng.uniform(*self.lifetime_range))
+        fade_spec = (int(self.rng.integers(3, 8)), int(self.rng.integers(8, 16)),
+                     float(self.rng.uniform(0, TWO_PI)), float(self.rng.uniform(0, TWO_PI)))
+        return EntityInstance(self.entity_type, q, now, lifetime, self.fade_in, self.fade_out,
+                              fade_spec, self.r_norm_all, self.n_phi)
+
+    @staticmethod
+    def _filament_death_age(entity):
+        for t in range(1, int(FILAMENT_MAX_LIFETIME) + 1):
+            if entity.density_factor(float(t)) < FILAMENT_DEATH_THRESHOLD:
+                return float(t)
+        return FILAMENT_MAX_LIFETIME
+
+    def seed_initial(self, now):
+        """Start at steady state: spawn target_count entities with staggered ages."""
+        n = max(self.target_count, 1)
+        for i in range(self.target_count):
+            e = self._spawn_one(now)
+            if e.entity_type == "filament":
+                span = max(self._filament_death_age(e) - FILAMENT_BIRTH_FADE_DUR, 1.0)
+                stagger = FILAMENT_BIRTH_FADE_DUR + span * (i / n)
+            else:
+                stagger = (e.fade_in + e.lifetime) * (i / n)
+            e.birth_time = now - stagger
+            self.entities.append(e)
+
+    def tick(self, now, dt):
+        self.entities = [e for e in self.entities if not e.is_dead(now)]
+        deficit = self.target_count - len(self.entities)
+        if deficit <= 0:
+            return
+        rate = self.target_count / (sum(self.lifetime_range) / 2.0)
+        self._spawn_debt += rate * dt
+        n_spawn = min(int(self._spawn_debt), deficit)
+        self._spawn_debt -= n_spawn
+        for _ in range(n_spawn):
+            self.entities.append(self._spawn_one(now))
+
+    @property
+    def alive_entities(self):
+        return self.entities
+
+
+# API-compatible spawn functions (reference: _spawn_single_*, render.py:1667-1866)
+def _spawn_single_filament(rng, n_r, n_phi, r_norm_all, omega_all):
+    q = draw_filament(rng, r_norm_all, omega_all)
+    e = np.empty((0, 0), dtype=np.float32)
+    return (np.arange(*q["rows"]), e, e, q["omega"], q["source_phi"], TWO_PI, q["sigma_r"],
+            q["sigma_phi0"], q["peak_density"], q["peak_temp"], q["base_r"])
+
+
+def _spawn_single_hotspot(rng, n_r, n_phi, r_norm_all, omega_all):
+    q = draw_hotspot(rng, r_norm_all, omega_all)
+    d, t = _profiles("hotspot", q, r_norm_all, n_phi)
+    return np.arange(*q["rows"]), d, t, q["omega"]
+
+
+def _spawn_single_rt_spike(rng, n_r, n_phi, r_norm_all, omega_all):
+    q = draw_rt_spike(rng, r_norm_all, omega_all)
+    d, t = _profiles("rt_spike", q, r_norm_all, n_phi)
+    return np.arange(*q["rows"]), d, t, q["omega"]
+
+
+def pack_entities(factories, now, n_r):
+    """Per-frame scalars of accumulate_entity_layer (render.py:3605-3642), one bhr_entity each.
+    All host arithmetic is Python float64 exactly as in the reference; per-texel work is the
+    device kernel's."""
+    out = []
+    for key in ("filament", "rt_spike", "hotspot"):
+        f = factories.get(key)
+        if f is None:
+            continue
+        for e in f.alive_entities:
+            age = now - e.birth_time
+            ent = L.BhrEntity()
+            ent.kind = KIND[e.entity_type]
+            ent.row_begin = max(int(e.q["rows"][0]), 0)
+            ent.row_end = min(int(e.q["rows"][1]), n_r)
+            ent.age = age
+            if e.entity_type == "filament":
+                if e.density_factor(age) < FILAMENT_DEATH_THRESHOLD:
+                    continue
+                s0 = max(e.blob_sigma_phi0, 1e-6)
+                sigma_t = s0 + e.alpha_shear * age
+                amp_d = e.blob_peak_density * s0 / sigma_t
+                amp_t = e.blob_peak_temp * s0 / sigma_t
+                birth = min(age / FILAMENT_BIRTH_FADE_DUR, 1.0) if FILAMENT_BIRTH_FADE_DUR > 0 else 1.0
+                cool = math.exp(-age / e.tau_cool) if e.tau_cool > 0 else 1.0
+                sigma_r = max(e.blob_sigma_r, 1e-6)
+                ent.scale = birth * cool
+                vals = [e.source_phi, e.blob_base_r, 0.5 / (sigma_r * sigma_r),
+                        0.5 / (sigma_t * sigma_t), amp_d * birth * cool, amp_t * birth * cool]
+            else:
+                alpha = e.fade_factor(now)
+                if alpha <= 0:
+                    continue
+                ent.scale = alpha
+                q = e.q
+                if e.entity_type == "hotspot":
+                    vals = [q["phi0"], q["r0"], q["phi_width"], q["r_width"], q["intensity"]]
+                else:
+                    vals = [q["phi0"], q["r0"], q["phi_width"], q["r_length"], q["intensity"],
+                            q["delta_T"]]
+            for i, v in enumerate(vals):
+                ent.p[i] = v
+            out.append(ent)
+    return out
+
+
+def init_lifecycle_system(renderer, n_r, n_phi, seed=42):
+    """_init_lifecycle_system (render.py:4079-4130): background parameters, three factories
+    (seeds +100/+200/+300, targets 200/30/15), staggered initial population, first texture."""
+    renderer.init_background_layer(n_r=n_r, n_phi=n_phi, seed=seed)
+    factories = make_factories(renderer.r_disk_inner, renderer.r_disk_outer, n_r, n_phi, seed)
+    renderer.generate_background(t=0.0)
+    renderer.accumulate_entity_layer(factories, now=0.0)
+    renderer.recompute_interactive_stats()
+    renderer.compose_interactive_texture()
+    return factories
+
+
+def make_factories(r_disk_inner, r_disk_outer, n_r, n_phi, seed=42):
+    """The three seeded, pre-populated factories of _init_lifecycle_system (host only)."""
+    r_norm_all = np.linspace(0, 1, n_r)
+    r_vals = r_disk_inner + (r_disk_outer - r_disk_inner) * r_norm_all
+    omega_all = np.sqrt(0.5 / (r_vals ** 3 + 1e-6)).astype(np.float32)
+    spec = [("filament", _spawn_single_filament, 200, (15.0, 60.0), 0.0, 0.0, 100),
+            ("hotspot", _spawn_single_hotspot, 30, (15.0, 30.0), 4.0, 4.0, 200),
+            ("rt_spike", _spawn_single_rt_spike, 15, (15.0, 30.0), 3.0, 3.0, 300)]
+    factories = {}
+    for name, fn, target, life, fin, fout, ds in spec:
+        factories[name] = EntityFactory(fn, target_count=target, lifetime_range=life, fade_in=fin,
+                                        fade_out=fout, n_r=n_r, n_phi=n_phi, r_norm_all=r_norm_all,
+                                        omega_all=omega_all, seed=seed + ds, entity_type=name)
+    for f in factories.values():
+        f.seed_initial(now=0.0)
+    return factories
+
+
+def advance_lifecycle_frame(renderer, factories, t, dt, recompute_stats=False, solo_idx=-1):
+    """_advance_lifecycle_frame (render.py:4133-4153): tick, background, entities, [stats], compose."""
+    for f in factories.values():
+        f.tick(now=t, dt=dt)
+    renderer.generate_background(t=t)
+    renderer.accumulate_entity_layer(factories, now=t)
+    if recompute_stats:
+        renderer.recompute_interactive_stats()
+    renderer.compose_interactive_texture(solo_idx=solo_idx)
+
+
+_init_lifecycle_system = init_lifecycle_system
+_advance_lifecycle_frame = advance_lifecycle_frame

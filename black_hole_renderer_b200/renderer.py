@@ -245,6 +245,11 @@ class Renderer:
         self._check(self._lib.bhr_last_total_steps(self._ctx, C.byref(v)))
         return v.value
 
+    def last_retrace_count(self):
+        v = C.c_uint32()
+        self._check(self._lib.bhr_last_retrace_count(self._ctx, C.byref(v)))
+        return v.value
+
     def last_stage_ms(self):
         arr = (C.c_float * 5)()
         self._check(self._lib.bhr_last_stage_ms(self._ctx, arr))

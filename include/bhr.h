@@ -71,7 +71,7 @@ typedef enum {
     BHR_BUF_HBLUR = 2,     /* bright_field after the horizontal pass: planar 3 x (H, W)  */
     BHR_BUF_FINAL = 3,     /* (H, W, 3) f32, render()'s return value                     */
     BHR_BUF_FINAL_U8 = 4,  /* (H, W, 3) u8 = trunc(clip(final) * 255), render.py:4463    */
-    BHR_BUF_CLASS = 5,     /* (H, W) u8: bits 0-1 termination (0 exhausted, 1 horizon, 2 escaped), bit 2 = disk hit */
+    BHR_BUF_CLASS = 5,     /* (H, W) u8: bits 0-1 termination (0 exhausted, 1 horizon, 2 escaped), bits 2-4 = min(disk hits, 7) */
     BHR_BUF_STEPS = 6,     /* (H, W) i32 RK4 evaluations per ray                         */
     BHR_BUF_DISK_TEX = 7,  /* disk_texture_field: (n_r, n_phi, 4) f32                    */
     BHR_BUF_DISK_MIPS = 8, /* compact pyramid, level l = (n_r>>l, n_phi>>l, 4) f32       */
@@ -87,8 +87,9 @@ int bhr_set_stream(bhr_ctx* ctx, void* cuda_stream); /* NULL = the context's own
 int bhr_synchronize(bhr_ctx* ctx);
 int bhr_set_lens_flare(bhr_ctx* ctx, int enabled);  /* renderer.lens_flare attribute */
 int bhr_version(void);
-/* tuning knobs for tests / benchmarks: "raymarch_mode" = 0 scalar FFMA, 1 packed FFMA2 (default),
- * 2 strict (reference operation order, exactly rounded; slow, for parity triage) */
+/* tuning knobs: "raymarch_mode" = 0 scalar FFMA, 1 packed FFMA2, 2 strict (reference operation
+ * order, exactly rounded; ~2x slower); "retrace_min_cross" = n: rays with >= n disk-plane
+ * crossings (photon-ring rays, chaotic) are re-traced by the strict integrator (default 3, 0 = off) */
 int bhr_set_option(bhr_ctx* ctx, const char* key, double value);
 /* pinned host memory so that frame read-back DMA needs no staging copy */
 int bhr_host_alloc(size_t bytes, void** out);
@@ -121,6 +122,8 @@ int bhr_buffer(bhr_ctx* ctx, int id, void** dev_ptr, size_t* bytes);
 int bhr_download(bhr_ctx* ctx, int id, void* host, size_t bytes);
 /* total RK4 evaluations of the last ray march (sum over pixels); feeds the flop count */
 int bhr_last_total_steps(bhr_ctx* ctx, uint64_t* out);
+/* number of rays the last ray march re-traced with the exactly-rounded integrator */
+int bhr_last_retrace_count(bhr_ctx* ctx, uint32_t* out);
 /* device time (ms, CUDA events) of the stages of the last bhr_render: {ray march, bloom H,
  * bloom V + composite, flare, total}; valid after bhr_synchronize */
 int bhr_last_stage_ms(bhr_ctx* ctx, float out[5]);

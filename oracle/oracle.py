@@ -294,3 +294,52 @@ def disk_texture_resolution(width, height, cam_pos, fov, r_inner, r_outer):
     n_phi += (16 - n_phi % 16) % 16
     n_r += (16 - n_r % 16) % 16
     return n_phi, n_r
+
+
+def accumulate_entities(factories, now, n_r, n_phi, omega_np, r_norm_all=None):
+    """accumulate_entity_layer's numpy body, render.py:3585-3649: returns staging (6, n_r, n_phi)
+    = comp[5:11].  Works on any objects with the reference's EntityInstance attributes."""
+    import math as _m
+    staging = np.zeros((6, n_r, n_phi), dtype=np.float32)
+    if r_norm_all is None:
+        r_norm_all = np.linspace(0, 1, n_r)
+    phi_arr = np.linspace(0, 2 * np.pi, n_phi, endpoint=False)
+    two_pi = 2 * np.pi
+    for key, d_idx, t_idx in (("filament", 0, 1), ("rt_spike", 2, 3), ("hotspot", 4, 5)):
+        factory = factories.get(key)
+        if factory is None:
+            continue
+        for e in factory.alive_entities:
+            age = now - e.birth_time
+            if e.entity_type == "filament":
+                if e.density_factor(age) < 0.008:
+                    continue
+                s0 = max(e.blob_sigma_phi0, 1e-6)
+                sig = s0 + e.alpha_shear * age
+                amp_d = e.blob_peak_density * s0 / sig
+                amp_t = e.blob_peak_temp * s0 / sig
+                birth = min(age / 5.0, 1.0)
+                cool = _m.exp(-age / e.tau_cool) if e.tau_cool > 0 else 1.0
+                sc_d, sc_t = amp_d * birth * cool, amp_t * birth * cool
+                i2p = 0.5 / (sig * sig)
+                sr = max(e.blob_sigma_r, 1e-6)
+                i2r = 0.5 / (sr * sr)
+                for ri in e.row_indices:
+                    if 0 <= ri < n_r:
+                        r_w = _m.exp(-(r_norm_all[ri] - e.blob_base_r) ** 2 * i2r)
+                        center = (e.source_phi - omega_np[ri] * age) % two_pi
+                        d_phi = phi_arr - center
+                        d_phi = d_phi - two_pi * np.round(d_phi / two_pi)
+                        prof = np.exp(-d_phi * d_phi * i2p)
+                        staging[d_idx, ri] += prof * (sc_d * r_w)
+                        staging[t_idx, ri] += prof * (sc_t * r_w)
+            else:
+                alpha = e.fade_factor(now)
+                if alpha <= 0:
+                    continue
+                for k, ri in enumerate(e.row_indices):
+                    if 0 <= ri < n_r:
+                        shift = int(age * omega_np[ri] / (2 * np.pi) * n_phi)
+                        staging[d_idx, ri] += np.roll(e.phi_density[k], -shift) * alpha
+                        staging[t_idx, ri] += np.roll(e.phi_temp[k], -shift) * alpha
+    return staging

@@ -1,0 +1,117 @@
+"""Host-side glue against fixtures produced by the reference's own host code (host.npz,
+texture_pipeline.npz): camera, texture sizing, skybox, lifecycle RNG streams, CLI."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from util import GOLDEN
+
+
+def test_build_camera():
+    from black_hole_renderer_b200 import build_camera
+    h = np.load(os.path.join(GOLDEN, "host.npz"))
+    for row in h["cameras"]:
+        pov, fov, w, hh = row[0:3], row[3], int(row[4]), int(row[5])
+        got = build_camera(pov, fov, w, hh)
+        flat = np.concatenate([got[0], got[1], got[2], got[3], [got[4], got[5]]])
+        assert np.array_equal(flat, row[6:])
+
+
+def test_disk_texture_resolution():
+    from black_hole_renderer_b200.driver import compute_disk_texture_resolution
+    h = np.load(os.path.join(GOLDEN, "host.npz"))
+    for row in h["tex_resolution"]:
+        w, hh, pov, fov, ri, ro = int(row[0]), int(row[1]), list(row[2:5]), row[5], row[6], row[7]
+        assert compute_disk_texture_resolution(w, hh, pov, fov, ri, ro) == (int(row[8]), int(row[9]))
+    # the sizes SURVEY.md section 8 quotes
+    assert compute_disk_texture_resolution(1920, 1080, [6, 0, 0.5], 90, 2.0, 15.0) == (2912, 416)
+
+
+def test_edge_alpha():
+    from black_hole_renderer_b200 import compute_edge_alpha
+    h = np.load(os.path.join(GOLDEN, "host.npz"))
+    assert np.array_equal(compute_edge_alpha(37), h["edge_alpha_37"])
+    assert np.array_equal(compute_edge_alpha(416), h["edge_alpha_416"])
+
+
+def test_skybox_bit_exact():
+    from black_hole_renderer_b200.skybox import generate_skybox
+    h = np.load(os.path.join(GOLDEN, "host.npz"))
+    small = generate_skybox(256, 128, seed=42, n_stars=200)
+    assert small.dtype == np.float32 and np.array_equal(small, h["skybox_256x128_s42_n200"])
+    full = generate_skybox(2048, 1024, seed=42, n_stars=6000)
+    assert hashlib.md5(full.astype(np.float32).tobytes()).hexdigest() == str(h["skybox_full_md5"][0])
+
+
+def _dump(f):
+    rows = []
+    for e in f.entities:
+        rows.append([e.birth_time, e.lifetime, e.omega, e.fade_in, e.fade_out, e.source_phi,
+                     e.alpha_shear, e.tau_cool, e.blob_base_r, e.blob_sigma_r, e.blob_sigma_phi0,
+                     e.blob_peak_density, e.blob_peak_temp, float(len(e.row_indices)),
+                     float(e.row_indices[0]), float(np.sum(e.phi_density, dtype=np.float64)),
+                     float(np.sum(e.phi_temp, dtype=np.float64)),
+                     float(np.sum(e.fade_noise, dtype=np.float64))])
+    return np.array(rows, dtype=np.float64).reshape(len(rows), 18)
+
+
+def test_lifecycle_rng_streams_match_reference():
+    """900 frames of spawn / cull: every entity parameter equals the reference's, i.e. the three
+    PCG64 streams are consumed in the same order."""
+    from black_hole_renderer_b200 import lifecycle as LC
+    t = np.load(os.path.join(GOLDEN, "texture_pipeline.npz"))
+    F = LC.make_factories(2.0, 15.0, 32, 128, 42)
+    for k in F:
+        assert np.array_equal(_dump(F[k]), t["init_factory_" + k]), k
+    for f in F.values():
+        f.tick(now=0.0, dt=0.0)
+    for frame in range(1, 900):
+        for f in F.values():
+            f.tick(now=frame * 0.1, dt=0.1)
+        if frame in (7, 25, 899):
+            for k in F:
+                assert np.array_equal(_dump(F[k]), t[f"f{frame}_factory_{k}"]), (frame, k)
+
+
+def test_entity_lifecycle_properties():
+    """Ported from the reference's tests/unit/test_entity_lifecycle.py: fade envelope, death."""
+    from black_hole_renderer_b200 import lifecycle as LC
+    F = LC.make_factories(2.0, 15.0, 64, 256, 7)
+    hs = F["hotspot"].entities[0]
+    b = hs.birth_time
+    assert hs.fade_factor(b - 1.0) == 0.0
+    assert abs(hs.fade_factor(b + hs.fade_in / 2) - 0.5) < 1e-9
+    assert hs.fade_factor(b + hs.fade_in + hs.lifetime / 2) == 1.0
+    assert hs.fade_factor(b + hs.total_duration + 0.1) == 0.0
+    assert hs.is_dead(b + hs.total_duration) and not hs.is_dead(b + hs.total_duration - 1e-6)
+    fl = F["filament"].entities[0]
+    assert fl.density_factor(0.0) == 1.0
+    assert fl.density_factor(10.0) > fl.density_factor(20.0) > 0
+    assert fl.is_dead(fl.birth_time + LC.FILAMENT_MAX_LIFETIME)
+    # steady state: the population stays at the target
+    for frame in range(600):
+        for f in F.values():
+            f.tick(now=frame * 0.1, dt=0.1)
+    assert 150 <= len(F["filament"].entities) <= 200
+    assert len(F["hotspot"].entities) <= 30 and len(F["rt_spike"].entities) <= 15
+
+
+def test_cli_surface():
+    import render
+    a = render.parse_args([])
+    assert (a.pov, a.fov, a.resolution, a.step_size, a.r_max, a.n_stars) == ([6, 0, 0.5], 90, "fhd", 0.1, 10, 6000)
+    assert (a.disk_inner_radius, a.disk_outer_radius, a.disk_tilt, a.anti_alias, a.aa_strength) == (2.0, 15.0, 0.0, "disabled", 1.0)
+    assert (a.n_frames, a.fps, a.orbit_degrees, a.disk_rotation_speed) == (3600, 36, 360.0, 0.1)
+    a = render.parse_args("--pov 4 3 2 --fov 75 -r 4k --ar1 1.5 --ar2 9 --disk_tilt 20 -s 0.02 --r_max 30 "
+                          "--anti_alias lod_radius --lens_flare --video --orbit --resume "
+                          "--disk_generation_scale 4 --force_regenerate_disk_texture "
+                          "--disk_rotation_algorithm keyframes --keyframes_count 3 -d gpu".split())
+    render.validate_args(a)
+    assert a.video and a.orbit and a.resume and a.lens_flare and a.disk_outer_radius == 9
+    for bad in (["--fov", "180"], ["--ar1", "5", "--ar2", "3"], ["-s", "0"], ["--aa_strength", "3"],
+                ["--n_frames", "0"], ["--fps", "0"], ["--orbit_degrees", "inf"],
+                ["--disk_texture", "x.png", "--video"]):
+        with pytest.raises(ValueError):
+            render.validate_args(render.parse_args(bad))

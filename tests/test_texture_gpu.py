@@ -1,0 +1,150 @@
+"""The on-device disk-texture pipeline (noise, background, entity layer, compose, mips) against
+the reference goldens and the oracle, plus the reference's own property tests
+(tests/unit/test_simplex_noise.py, test_background_layer.py, test_entity_accumulate.py)."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle as O
+from util import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+def _renderer(n_r=32, n_phi=128, **kw):
+    from black_hole_renderer_b200 import Renderer
+    return Renderer(16, 8, np.zeros((8, 16, 3), np.float32), np.zeros((n_r, n_phi, 4), np.float32), **kw)
+
+
+def test_noise_bit_exact_with_reference():
+    d = np.load(os.path.join(GOLDEN, "noise.npz"))
+    r = _renderer()
+    assert np.array_equal(r.eval_noise(d["coords"], "simplex"), d["simplex"])
+    for k in d.files:
+        if k.startswith("fbm_"):
+            _, o, p, l = k.split("_")
+            got = r.eval_noise(d["coords"], "fbm", int(o), float(p), float(l))
+            assert np.abs(got - d[k]).max() <= 3e-7, k
+
+
+def test_noise_reference_properties():
+    r = _renderer()
+    rng = np.random.RandomState(123)
+    c = rng.uniform(-100, 100, size=(5000, 3)).astype(np.float32)
+    v = r.eval_noise(c, mode="simplex")
+    assert np.all(v >= -1.01) and np.all(v <= 1.01) and np.std(v) > 0.05
+    assert np.array_equal(v, r.eval_noise(c, mode="simplex"))
+    c = rng.uniform(-10, 10, size=(500, 3)).astype(np.float32)
+    np.testing.assert_allclose(r.eval_noise(c, "simplex"),
+                               r.eval_noise(c, "fbm", octaves=1, persistence=1.0, lacunarity=2.0), atol=1e-5)
+    n = 50
+    rv = np.linspace(0.1, 1.0, n)
+    c0 = np.column_stack([np.cos(0.0) * 8 * np.ones(n), np.sin(0.0) * 8 * np.ones(n), rv * 8 + 0.5]).astype(np.float32)
+    c1 = np.column_stack([np.cos(2 * np.pi) * 8 * np.ones(n), np.sin(2 * np.pi) * 8 * np.ones(n), rv * 8 + 0.5]).astype(np.float32)
+    np.testing.assert_allclose(r.eval_noise(c0), r.eval_noise(c1), atol=1e-5)
+    assert np.array_equal(r.eval_noise(c, "simplex"), O.eval_noise(c, "simplex"))
+    assert r.eval_noise(np.zeros((0, 3), np.float32)).shape == (0,)
+
+
+def test_lifecycle_pipeline_matches_reference_goldens():
+    """_init_lifecycle_system + 25 video frames: comp planes, stats, RGBA texture, mips."""
+    from black_hole_renderer_b200 import lifecycle as LC
+    t = np.load(os.path.join(GOLDEN, "texture_pipeline.npz"))
+    n_r, n_phi = 32, 128
+    r = _renderer(n_r, n_phi)
+    F = LC.init_lifecycle_system(r, n_r, n_phi, seed=42)
+    assert r._bg_az_freq == int(t["az_freq"][0]) and r._bg_az_shear == float(t["az_shear"][0])
+    comp = r._comp_field.to_numpy()
+    assert np.abs(comp - t["init_comp"]).max() <= 1e-6
+    assert np.abs(comp[5:11] - t["init_comp"][5:11]).max() <= 1.2e-7      # entity planes
+    np.testing.assert_allclose(r._param_stats_field.to_numpy(), t["init_stats"], rtol=1e-5)
+    np.testing.assert_allclose(r._param_row_stats_field.to_numpy(), t["init_row_stats"], atol=1e-6)
+    assert np.abs(r.disk_texture_field.to_numpy() - t["init_tex"]).max() <= 2e-5
+    LC.advance_lifecycle_frame(r, F, t=0.0, dt=0.0, recompute_stats=True)
+    assert np.abs(r.disk_texture_field.to_numpy() - t["f0_tex"]).max() <= 2e-5
+    for frame in range(1, 26):
+        tt = frame * 0.1
+        for f in F.values():
+            f.tick(now=tt, dt=0.1)
+        if frame in (7, 25):
+            r.generate_background(t=tt)
+            r.accumulate_entity_layer(F, now=tt)
+            if frame == 25:
+                r.recompute_interactive_stats()
+            r.compose_interactive_texture()
+            k = f"f{frame}"
+            comp = r._comp_field.to_numpy()
+            assert np.abs(comp - t[k + "_comp"]).max() <= 1e-6, k
+            assert (comp[5:11] == t[k + "_comp"][5:11]).mean() > 0.999
+            np.testing.assert_allclose(r._param_stats_field.to_numpy(), t[k + "_stats"], rtol=1e-5)
+            assert np.abs(r.disk_texture_field.to_numpy() - t[k + "_tex"]).max() <= 2e-5, k
+            assert np.abs(r.disk_mips_field.to_numpy() - t[k + "_mips"]).max() <= 2e-5, k
+
+
+def test_background_reference_properties():
+    """tests/unit/test_background_layer.py: plane ranges / relations, untouched entity planes,
+    temporal evolution."""
+    r = _renderer(64, 256)
+    r.init_background_layer(64, 256, seed=42)
+    with_entities = np.random.default_rng(0).random((13, 64, 256)).astype(np.float32)
+    r._check(r._lib.bhr_upload_comp(r._ctx, with_entities.ctypes.data_as(
+        __import__("ctypes").POINTER(__import__("ctypes").c_float))))
+    r.generate_background(0.0)
+    c0 = r._comp_field.to_numpy()
+    assert np.array_equal(c0[5:11], with_entities[5:11])
+    assert np.all(c0[1] == 0) and np.all(c0[2] == 0)
+    assert c0[0].min() >= 0 and c0[0].max() <= 0.25 + 1e-6
+    assert c0[3].min() >= 0 and c0[3].max() <= 1
+    np.testing.assert_allclose(c0[4], 0.05 * c0[3], atol=1e-7)
+    assert c0[11].min() >= 0 and c0[11].max() <= 1 and c0[12].min() >= 0.1 and c0[12].max() <= 1
+    r.generate_background(5.0)
+    c5 = r._comp_field.to_numpy()
+    assert np.abs(c5[3] - c0[3]).mean() > 1e-3
+    r.generate_background(5.01)
+    assert np.abs(r._comp_field.to_numpy()[0] - c5[0]).mean() < 1e-3
+    want = c0.copy()
+    O.generate_background(want, r._bg_az_freq, r._bg_az_shear, 2.0, 15.0, 0.0)
+    assert np.abs(want - c0).max() <= 1e-6
+
+
+def test_entity_layer_against_oracle_larger_texture():
+    from black_hole_renderer_b200 import lifecycle as LC
+    n_r, n_phi = 144, 976          # the sd texture of BASELINE.json configs[0]
+    r = _renderer(n_r, n_phi)
+    r.init_background_layer(n_r, n_phi, seed=42)
+    F = LC.make_factories(2.0, 15.0, n_r, n_phi, 42)
+    for frame in range(40):
+        for f in F.values():
+            f.tick(now=frame * 0.1, dt=0.1)
+    now = 3.9
+    r.accumulate_entity_layer(F, now)
+    got = r._comp_field.to_numpy()[5:11]
+    want = O.accumulate_entities(F, now, n_r, n_phi, r._bg_omega_all_np)
+    assert np.abs(got - want).max() <= 2.4e-7
+    assert (got == want).mean() > 0.999
+    assert got.min() >= 0 and got[0].max() > 0.1
+    # empty factories zero the planes (tests/unit/test_entity_accumulate.py)
+    for f in F.values():
+        f.entities = []
+    r.accumulate_entity_layer(F, now)
+    assert np.all(r._comp_field.to_numpy()[5:11] == 0)
+    with pytest.raises(AssertionError):
+        _renderer(32, 128).generate_background(0.0)
+
+
+def test_compose_against_oracle():
+    r = _renderer(64, 256)
+    r.init_background_layer(64, 256, seed=3)
+    comp = np.random.default_rng(1).random((13, 64, 256)).astype(np.float32)
+    import ctypes as C
+    r._check(r._lib.bhr_upload_comp(r._ctx, comp.ctypes.data_as(C.POINTER(C.c_float))))
+    r.recompute_interactive_stats()
+    s, rs = O.interactive_stats(comp, r._bg_edge_np)
+    assert np.array_equal(s, r._param_stats_field.to_numpy())
+    assert np.array_equal(rs, r._param_row_stats_field.to_numpy())
+    r.compose_interactive_texture()
+    want = O.compose_texture(comp, r._bg_omega_all_np, r._bg_edge_np, s, rs)
+    got = r.disk_texture_field.to_numpy()
+    assert np.abs(got - want).max() <= 2e-5
+    assert np.abs(r.disk_mips_field.to_numpy() - O.build_mips(got, 5, numpy_order=False)).max() <= 1e-7
