@@ -1,0 +1,93 @@
+"""Host-side logic of the multi-GPU paths on CPU: row tiling + halo exchange + gather with the
+gloo backend (world_size 2 and 3), frame sharding of the video driver."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _truth(C, H, W):
+    y = torch.arange(H, dtype=torch.float32)[None, :, None]
+    x = torch.arange(W, dtype=torch.float32)[None, None, :]
+    c = torch.arange(C, dtype=torch.float32)[:, None, None]
+    return 1000 * c + y + 0.001 * x
+
+
+def _worker(rank, world, port, H, W, radius, result_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from black_hole_renderer_b200.dist import exchange_halos, gather_rows, tile_rows
+    C = 3
+    truth = _truth(C, H, W)
+    row0, row1 = tile_rows(H, world, rank)
+    plane = torch.full((C, H, W), -1.0)
+    plane[:, row0:row1] = truth[:, row0:row1]
+    exchange_halos(plane, H, radius, rank, world)
+    lo, hi = max(row0 - radius, 0), min(row1 + radius, H)
+    ok = bool(torch.equal(plane[:, lo:hi], truth[:, lo:hi]))
+    # rows outside tile + halo must be untouched
+    untouched = bool((plane[:, :lo] == -1).all() and (plane[:, hi:] == -1).all())
+    tile = truth[0, row0:row1].unsqueeze(-1).repeat(1, 1, 3).contiguous()
+    full = gather_rows(tile, H, rank, world, 0)
+    gathered = True
+    if rank == 0:
+        gathered = bool(torch.equal(full, truth[0].unsqueeze(-1).repeat(1, 1, 3)))
+    else:
+        gathered = full is None
+    with open(os.path.join(result_dir, f"r{rank}"), "w") as f:
+        f.write(f"{int(ok)}{int(untouched)}{int(gathered)}")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,H,radius", [(2, 64, 7), (3, 50, 12), (3, 20, 9)])
+def test_halo_exchange_and_gather_gloo(tmp_path, world, H, radius):
+    """(3, 20, 9): tiles of 6-7 rows are shorter than the radius, so halos span two ranks."""
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, H, 16, radius, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert open(tmp_path / f"r{r}").read() == "111", r
+
+
+def test_tile_rows_partition():
+    from black_hole_renderer_b200.dist import owners_of_rows, tile_rows
+    for H in (2160, 1080, 37, 8):
+        for world in (1, 2, 3, 4, 8):
+            rows = [tile_rows(H, world, r) for r in range(world)]
+            assert rows[0][0] == 0 and rows[-1][1] == H
+            assert all(rows[i][1] == rows[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in rows]
+            assert max(sizes) - min(sizes) <= 1
+            cover = owners_of_rows(H, world, -5, H + 5)
+            assert sum(b - a for _, a, b in cover) == H
+
+
+def test_frame_sharding_blocks_of_60():
+    from black_hole_renderer_b200.driver import STATS_PERIOD, frame_owner, orbit_camera
+    n = 3600
+    for world in (1, 2, 4, 8):
+        owners = [frame_owner(f, world) for f in range(n)]
+        assert set(owners) == set(range(world))
+        # a rank owns whole stats blocks, so the frame that recomputes the statistics
+        # (frame % 60 == 0, render.py:4457) is rendered by the rank that uses them
+        for f in range(n):
+            assert owners[f] == owners[f - f % STATS_PERIOD]
+        counts = np.bincount(owners, minlength=world)
+        assert counts.max() - counts.min() <= STATS_PERIOD
+    # orbit camera: radius = |pov| (3-D norm), height = pov.z
+    cam = orbit_camera([6, 0, 0.5], 900, 3600, 360.0)
+    assert abs(np.hypot(cam[0], cam[1]) - np.sqrt(36.25)) < 1e-12 and cam[2] == 0.5
+    assert abs(cam[0]) < 1e-9 and cam[1] > 0

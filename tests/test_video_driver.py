@@ -1,0 +1,92 @@
+"""render_video's camera path, resume protocol and frame sharding with a fake renderer (the
+approach of the reference's tests/unit/test_orbit_degrees.py: no rendering, no GPU)."""
+import json
+import os
+
+import numpy as np
+
+
+class FakeRenderer:
+    def __init__(self, n_r=32, n_phi=128):
+        self.dtex_h, self.dtex_w = n_r, n_phi
+        self.r_disk_inner, self.r_disk_outer = 2.0, 15.0
+        self.cams, self.stats_calls, self.bg_times = [], 0, []
+
+    def init_background_layer(self, n_r, n_phi, seed=42): pass
+    def generate_background(self, t): self.bg_times.append(t)
+    def accumulate_entity_layer(self, factories, now): pass
+    def recompute_interactive_stats(self): self.stats_calls += 1
+    def compose_interactive_texture(self, solo_idx=-1): pass
+
+    def render_u8(self, cam_pos, fov, frame=0):
+        self.cams.append(list(cam_pos))
+        return np.zeros((4, 8, 3), dtype=np.uint8)
+
+
+def _run(tmp_path, renderer, n_frames=12, resume=False, rank=0, world=1, orbit=True, degrees=90.0):
+    from black_hole_renderer_b200.driver import render_video
+    out = str(tmp_path / "v.mp4")
+    render_video(renderer, 8, 4, n_frames=n_frames, fps=4, output_path=out, fov=90.0,
+                 static_cam_pos=[6, 0, 0.5], orbit=orbit, resume=resume, disk_rotation_speed=0.1,
+                 orbit_degrees=degrees, rank=rank, world_size=world)
+    frames_dir = [d for d in os.listdir(tmp_path) if d.startswith(".frames_")][0]
+    return tmp_path / frames_dir
+
+
+def test_orbit_camera_path_and_files(tmp_path):
+    r = FakeRenderer()
+    d = _run(tmp_path, r, n_frames=12, degrees=90.0)
+    assert len(r.cams) == 12
+    radius = np.sqrt(36.25)
+    for f, cam in enumerate(r.cams):
+        a = np.radians(f * 90.0 / 12)
+        np.testing.assert_allclose(cam, [radius * np.cos(a), radius * np.sin(a), 0.5], atol=1e-12)
+    assert sorted(p for p in os.listdir(d) if p.endswith(".png")) == [f"frame_{f:04d}.png" for f in range(12)]
+    prog = json.load(open(d / "progress.json"))
+    assert sorted(prog["completed"]) == list(range(12))
+    assert prog["params"] == {"n_frames": 12, "fov": 90.0, "orbit": True, "disk_rotation_speed": 0.1,
+                              "orbit_degrees": 90.0}
+    # init (1) + frame 0 (frame % 60 == 0)
+    assert r.stats_calls == 2
+    # negative orbit_degrees reverses the direction (reference test_orbit_degrees.py)
+    r2 = FakeRenderer()
+    _run(tmp_path / "neg" if (tmp_path / "neg").mkdir() is None else tmp_path, r2, n_frames=4, degrees=-40.0)
+    assert r2.cams[1][1] < 0
+
+
+def test_resume_skips_completed_and_replays_lifecycle(tmp_path):
+    r = FakeRenderer()
+    d = _run(tmp_path, r, n_frames=10)
+    prog = json.load(open(d / "progress.json"))
+    prog["completed"] = [0, 1, 2, 3, 4]
+    json.dump(prog, open(d / "progress.json", "w"))
+    r2 = FakeRenderer()
+    _run(tmp_path, r2, n_frames=10, resume=True)
+    assert len(r2.cams) == 5                       # frames 5..9 only
+    # replay of frames 0..4 (render.py:4427-4434) + the five new frames + init
+    assert len(r2.bg_times) == 1 + 5 + 5
+    # changed parameters restart from scratch
+    r3 = FakeRenderer()
+    _run(tmp_path, r3, n_frames=10, resume=True, degrees=180.0)
+    assert len(r3.cams) == 10
+
+
+def test_static_camera_and_sharding(tmp_path):
+    r = FakeRenderer()
+    _run(tmp_path, r, n_frames=5, orbit=False)
+    assert all(c == [6, 0, 0.5] for c in r.cams)
+    # two ranks, 150 frames: blocks of 60 -> rank 0 renders 0-59 and 120-149, rank 1 renders 60-119
+    a, b = FakeRenderer(), FakeRenderer()
+    (tmp_path / "s").mkdir()
+    from black_hole_renderer_b200.driver import render_video
+    out = str(tmp_path / "s" / "v.mp4")
+    kw = dict(n_frames=150, fps=4, output_path=out, fov=90.0, static_cam_pos=[6, 0, 0.5], orbit=True,
+              disk_rotation_speed=0.1, orbit_degrees=360.0, world_size=2)
+    render_video(b, 8, 4, rank=1, **kw)
+    render_video(a, 8, 4, rank=0, **kw)
+    assert len(a.cams) == 90 and len(b.cams) == 60
+    d = [x for x in os.listdir(tmp_path / "s") if x.startswith(".frames_")][0]
+    prog = json.load(open(tmp_path / "s" / d / "progress.json"))
+    assert sorted(prog["completed"]) == list(range(150))
+    # every rank recomputes the statistics on the first frame of each block it owns
+    assert a.stats_calls == 1 + 2 and b.stats_calls == 1 + 1
