@@ -102,8 +102,9 @@ def run_reference(args):
     from util import synthetic_disk_texture
     tex = synthetic_disk_texture(n_r, n_phi)      # texel values do not affect the CPU timing
     times = []
+    all_threads = os.cpu_count() or 1         # torchrun exports OMP_NUM_THREADS=1: use every host thread
     for i in range(args.warmup + args.steps):
-        dt, steps, threads = cpu_port_frame(W, H, sky, tex)
+        dt, steps, threads = cpu_port_frame(W, H, sky, tex, threads=all_threads)
         if i >= args.warmup:
             times.append(dt)
     ms = 1e3 * float(np.mean(times))
@@ -249,7 +250,7 @@ def main():
         "e2e": {"value": rays / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_frame": e2e_ms,
                 "h2d_bytes_per_step": 64, "d2h_bytes_per_step": W * H * 12,
                 "note": "Renderer.render(cam, fov, out=pinned (H,W,3) f32): camera struct H2D, frame D2H, host sync"},
-        "gpu_launches": 3 * args.steps * world,
+        "gpu_launches": 4 * args.steps * world,   # raymarch, retrace, bloom_h, bloom_v_composite per frame
         "roofline": {"bound": "fp32", "kernel": "raymarch_kernel", "achieved": achieved, "peak": peak,
                      "unit": "TFLOP/s", "frac": (achieved / peak) if peak else None, "traffic": None,
                      "algorithmic": f"{FLOP_PER_STEP} flop/RK4 step x {total_steps} steps (SURVEY.md 8d)",
@@ -257,12 +258,12 @@ def main():
                                     "MEASURED_PEAKS.json holds no FP32 figure"},
         "clocks": clocks,
     }
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:      # CPU baseline: rank 0 at N = 1 only
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         tex = r.disk_texture_field.to_numpy()
         times = []
         for _ in range(3):
-            dt, _, threads = cpu_port_frame(W, H, sky, tex)
+            dt, _, threads = cpu_port_frame(W, H, sky, tex, threads=os.cpu_count() or 1)
             times.append(dt)
         line["cpu_baseline"] = {"value": W * H / min(times[1:]) / 1e6, "unit": "Mrays/s", "cores": threads,
                                 "kind": "port", "ms_per_frame": 1e3 * min(times[1:]),
