@@ -96,8 +96,11 @@ __device__ __forceinline__ double np_mod(double a, double b) {   // numpy.mod fo
     return m;
 }
 
+// Every term is zero for most pixels; the squared-distance / slope pre-tests below skip the
+// sqrt / atan2 / exp of terms that cannot contribute (a skipped term adds exactly 0, as in numpy).
 __device__ void flare_pixel(const FlareParams& F, int x, int y, float fl[3]) {
     const double PI = 3.14159265358979323846;
+    const double GUARD = 1.0 + 1e-9;
     fl[0] = fl[1] = fl[2] = 0.0f;
     const double gc[3] = {1.0, 0.9, 0.7};
     for (int g = 0; g < 8; ++g) {
@@ -105,7 +108,9 @@ __device__ void flare_pixel(const FlareParams& F, int x, int y, float fl[3]) {
         double gx = F.light_x + (F.scx - F.light_x) * t, gy = F.light_y + (F.scy - F.light_y) * t;
         double size = (25 + g * 30) * F.scale;
         double dx = x - gx, dy = y - gy;
-        double dist = sqrt(dx * dx + dy * dy);
+        double d2 = dx * dx + dy * dy;
+        if (d2 >= size * size * GUARD) continue;
+        double dist = sqrt(d2);
         float alpha = 0.0f;
         if (dist < size) { double u = 1 - dist / size; alpha = (float)(u * u * (1 - g * 0.08) * F.intensity); }
         for (int c = 0; c < 3; ++c) fl[c] = (float)((double)fl[c] + (double)alpha * gc[c]);
@@ -116,7 +121,10 @@ __device__ void flare_pixel(const FlareParams& F, int x, int y, float fl[3]) {
         double rx = F.light_x + (F.scx - F.light_x) * t, ry = F.light_y + (F.scy - F.light_y) * t;
         double rr = (60 + k * 40) * F.scale, rw = (6 + k * 3) * F.scale;
         double dx = x - rx, dy = y - ry;
-        double dist = sqrt(dx * dx + dy * dy);
+        double d2 = dx * dx + dy * dy;
+        double lo = rr - rw, hi = rr + rw;
+        if (d2 >= hi * hi * GUARD || (lo > 0 && d2 * GUARD <= lo * lo)) continue;
+        double dist = sqrt(d2);
         double u = fmin(fmax(1 - fabs(dist - rr) / rw, 0.0), 1.0);
         double ra = u * u * 0.5 * F.intensity * (1 - k * 0.25);
         for (int c = 0; c < 3; ++c) fl[c] = (float)((double)fl[c] + ra * rc[k][c]);
@@ -124,49 +132,67 @@ __device__ void flare_pixel(const FlareParams& F, int x, int y, float fl[3]) {
     {
         const double hc[3] = {0.6, 0.7, 1.0};
         double hx = F.light_x + (F.scx - F.light_x) * 0.5, hy = F.light_y + (F.scy - F.light_y) * 0.5;
-        double hr = 100 * F.scale;
+        double hr = 100 * F.scale, hw = 15 * F.scale;
         double dx = x - hx, dy = y - hy;
-        double angle = atan2(dy, dx);
-        double dist = sqrt(dx * dx + dy * dy);
-        double edge = fabs(np_mod(angle, PI / 3) - PI / 6);
-        double hf = fmin(fmax(1 - edge / 0.2, 0.0), 1.0);
-        double u = fmin(fmax(1 - fabs(dist - hr) / (15 * F.scale), 0.0), 1.0);
-        double ra = u * u * hf * 0.3 * F.intensity;
-        for (int c = 0; c < 3; ++c) fl[c] = (float)((double)fl[c] + ra * hc[c]);
+        double d2 = dx * dx + dy * dy;
+        double lo = hr - hw, hi = hr + hw;
+        if (!(d2 >= hi * hi * GUARD || (lo > 0 && d2 * GUARD <= lo * lo))) {
+            double angle = atan2(dy, dx);
+            double dist = sqrt(d2);
+            double edge = fabs(np_mod(angle, PI / 3) - PI / 6);
+            double hf = fmin(fmax(1 - edge / 0.2, 0.0), 1.0);
+            double u = fmin(fmax(1 - fabs(dist - hr) / hw, 0.0), 1.0);
+            double ra = u * u * hf * 0.3 * F.intensity;
+            for (int c = 0; c < 3; ++c) fl[c] = (float)((double)fl[c] + ra * hc[c]);
+        }
     }
     {
         const double sc[3] = {1.0, 0.95, 0.9};
         const double main_angles[4] = {0.0, PI / 2, PI, 3 * PI / 2};
         double dx = x - F.light_x, dy = y - F.light_y;
-        double dist = sqrt(dx * dx + dy * dy);
-        double angle = atan2(dy, dx);
-        double falloff = exp(-dist / F.streak_len);
-        for (int a = 0; a < 4; ++a) {
-            double diff = fabs(np_mod(angle - main_angles[a] + PI, 2 * PI) - PI);
-            for (int c = 0; c < 3; ++c) {
-                double add = diff < 0.05 ? falloff * F.streak_alpha * sc[c] : 0.0;
-                fl[c] = (float)((double)fl[c] + add);
+        // within 0.05 rad of one of the four axes through the light?  tan(0.05) = 0.050041708
+        const double T = 0.0500418 * GUARD;
+        if (fabs(dy) <= T * fabs(dx) || fabs(dx) <= T * fabs(dy)) {
+            double dist = sqrt(dx * dx + dy * dy);
+            double angle = atan2(dy, dx);
+            double falloff = exp(-dist / F.streak_len);
+            for (int a = 0; a < 4; ++a) {
+                double diff = fabs(np_mod(angle - main_angles[a] + PI, 2 * PI) - PI);
+                for (int c = 0; c < 3; ++c) {
+                    double add = diff < 0.05 ? falloff * F.streak_alpha * sc[c] : 0.0;
+                    fl[c] = (float)((double)fl[c] + add);
+                }
             }
         }
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// V pass + composite.  block = 32 (x) x 8 (row groups); each thread: column x, P_OUT rows.
+// V pass + composite.  block = 32 (x) x 8 (row groups) threads, tile = 32 columns x 64 rows.
+// Per channel the block stages the (64 + 2R) x 32 samples it needs in shared memory (coalesced
+// rows, zero outside the image; 2.2x re-read instead of 10x), then each thread slides its
+// 8-output window down the column.  Composite, flare and the f32 / u8 stores are fused in.
 // ---------------------------------------------------------------------------------------------
+constexpr int V_TILE_ROWS = 8 * P_OUT;   // 64
+
 template <bool BLOOM>
 __global__ void __launch_bounds__(256) bloom_v_composite_kernel(
     const float* __restrict__ hblur, const float* __restrict__ bg, const float* __restrict__ disk,
     float* __restrict__ blur_out, float* __restrict__ final_f32, uint8_t* __restrict__ final_u8,
     int W, int H, int row0, int row1, int R, const float* __restrict__ wtab, int wtab_stride,
     const float* __restrict__ wsum_y, size_t plane, FlareParams F) {
-    extern __shared__ float wsh[];   // 3 x wtab_stride
+    extern __shared__ float vsm[];
+    const int nk = (2 * R + P_OUT + P_OUT - 1) / P_OUT * P_OUT;    // window positions, padded
+    const int tile_rows = V_TILE_ROWS - P_OUT + nk;                // rows any thread may touch
+    float* wsh = vsm;                                              // 3 x wtab_stride weights
+    float* tile = vsm + 3 * wtab_stride;                           // tile_rows x 32
+    const int tid = threadIdx.y * 32 + threadIdx.x;
     if (BLOOM)
-        for (int k = threadIdx.x + threadIdx.y * 32; k < 3 * wtab_stride; k += 256) wsh[k] = wtab[k];
-    __syncthreads();
+        for (int k = tid; k < 3 * wtab_stride; k += 256) wsh[k] = wtab[k];
     const int x = blockIdx.x * 32 + threadIdx.x;
-    const int y0 = row0 + (blockIdx.y * 8 + threadIdx.y) * P_OUT;
-    if (x >= W || y0 >= row1) return;
+    const int ty0 = row0 + blockIdx.y * V_TILE_ROWS;               // first output row of the tile
+    const int y0 = ty0 + threadIdx.y * P_OUT;                      // first output row of this thread
+    const bool col_ok = x < W;
 
     float val[3][P_OUT];
 #pragma unroll
@@ -175,18 +201,23 @@ __global__ void __launch_bounds__(256) bloom_v_composite_kernel(
 #pragma unroll
         for (int p = 0; p < P_OUT; ++p) { acc[p] = 0.0f; wr[p] = 0.0f; }
         if (BLOOM) {
-            const float* col = hblur + c * plane + x;
+            __syncthreads();                                       // previous channel's tile is consumed
+            const float* src = hblur + c * plane;
+            for (int r = threadIdx.y; r < tile_rows; r += 8) {
+                const int y = ty0 - R + r;
+                tile[r * 32 + threadIdx.x] = (col_ok && y >= 0 && y < H) ? __ldg(src + (size_t)y * W + x) : 0.0f;
+            }
+            __syncthreads();
             const float* wc = wsh + c * wtab_stride;
-            const int nk = (2 * R + P_OUT + P_OUT - 1) / P_OUT * P_OUT;
+            const float* colp = tile + threadIdx.y * P_OUT * 32 + threadIdx.x;
             for (int k0 = 0; k0 < nk; k0 += P_OUT) {
 #pragma unroll
                 for (int kk = 0; kk < P_OUT; ++kk) {
                     const int k = k0 + kk;
-                    const int y = y0 - R + k;
 #pragma unroll
                     for (int p = P_OUT - 1; p > 0; --p) wr[p] = wr[p - 1];
                     wr[0] = wc[k];
-                    const float v = (y >= 0 && y < H) ? __ldg(col + (size_t)y * W) : 0.0f;
+                    const float v = colp[k * 32];
 #pragma unroll
                     for (int p = 0; p < P_OUT; ++p) acc[p] = fmaf(v, wr[p], acc[p]);
                 }
@@ -196,7 +227,8 @@ __global__ void __launch_bounds__(256) bloom_v_composite_kernel(
         for (int p = 0; p < P_OUT; ++p) {
             const int y = y0 + p;
             float b = 0.0f;
-            if (y < row1) {
+            val[c][p] = 0.0f;
+            if (col_ok && y < row1) {
                 const size_t o = c * plane + (size_t)y * W + x;
                 float v = bg[o] + disk[o];
                 if (BLOOM) {
@@ -209,6 +241,7 @@ __global__ void __launch_bounds__(256) bloom_v_composite_kernel(
             }
         }
     }
+    if (!col_ok) return;
 #pragma unroll
     for (int p = 0; p < P_OUT; ++p) {
         const int y = y0 + p;
@@ -350,7 +383,10 @@ int bhr_launch_bloom_v_composite(bhr_ctx* ctx, uint32_t flags, int row0, int row
             ctx->hblur, ctx->bg, ctx->disk, nullptr, ctx->final_f32, ctx->final_u8, W, H, row0, row1, ctx->bloom_R,
             ctx->d_wtab, ctx->wtab_stride, ctx->d_wsum_y, plane, F);
     } else {
-        size_t smem = (size_t)3 * ctx->wtab_stride * sizeof(float);
+        const int nk = (2 * ctx->bloom_R + P_OUT + P_OUT - 1) / P_OUT * P_OUT;
+        size_t smem = ((size_t)3 * ctx->wtab_stride + (size_t)(V_TILE_ROWS - P_OUT + nk) * 32) * sizeof(float);
+        if (smem > 48 * 1024)
+            BHR_CUDA(ctx, cudaFuncSetAttribute(bloom_v_composite_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         bloom_v_composite_kernel<true><<<grid, block, smem, ctx->stream>>>(
             ctx->hblur, ctx->bg, ctx->disk, ctx->blur, ctx->final_f32, ctx->final_u8, W, H, row0, row1, ctx->bloom_R,
             ctx->d_wtab, ctx->wtab_stride, ctx->d_wsum_y, plane, F);
