@@ -250,8 +250,8 @@ def main():
         "e2e": {"value": rays / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_frame": e2e_ms,
                 "h2d_bytes_per_step": 64, "d2h_bytes_per_step": W * H * 12,
                 "note": "Renderer.render(cam, fov, out=pinned (H,W,3) f32): camera struct H2D, frame D2H, host sync"},
-        "gpu_launches": 4 * args.steps * world,   # raymarch, retrace, bloom_h, bloom_v_composite per frame
-        "roofline": {"bound": "fp32", "kernel": "raymarch_kernel", "achieved": achieved, "peak": peak,
+        "gpu_launches": 6 * args.steps * world,   # band_list, raymarch_persistent, retrace, bloom_h, bloom_v, composite per frame
+        "roofline": {"bound": "fp32", "kernel": "raymarch_persistent (+ band_list, retrace)", "achieved": achieved, "peak": peak,
                      "unit": "TFLOP/s", "frac": (achieved / peak) if peak else None, "traffic": None,
                      "algorithmic": f"{FLOP_PER_STEP} flop/RK4 step x {total_steps} steps (SURVEY.md 8d)",
                      "peak_source": "scalar FFMA microbenchmark measured in this run (bhr_measure_fp32_peak); "

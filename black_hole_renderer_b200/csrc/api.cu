@@ -60,8 +60,12 @@ extern "C" int bhr_create(const bhr_config* cfg, bhr_ctx** out) {
     CREATE_CHECK(cudaMalloc(&ctx->steps, plane * sizeof(int)));
     CREATE_CHECK(cudaMalloc(&ctx->d_total_steps, sizeof(unsigned long long)));
     CREATE_CHECK(cudaMalloc(&ctx->d_flare_sums, 3 * sizeof(double)));
-    CREATE_CHECK(cudaMalloc(&ctx->retrace_queue, plane * sizeof(unsigned long long)));
-    CREATE_CHECK(cudaMemset(ctx->retrace_queue, 0, plane * sizeof(unsigned long long)));
+    // [0, plane) u64 re-trace entries of the safety net; then plane i32 band pixels
+    CREATE_CHECK(cudaMalloc(&ctx->retrace_queue, plane * (sizeof(unsigned long long) + sizeof(int))));
+    CREATE_CHECK(cudaMemset(ctx->retrace_queue, 0, plane * (sizeof(unsigned long long) + sizeof(int))));
+    CREATE_CHECK(cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, cfg->device));
+    ctx->persistent = 1;
+    ctx->pblock_big = 1;
     CREATE_CHECK(cudaMalloc(&ctx->d_queue_count, 4 * sizeof(unsigned int)));
     CREATE_CHECK(cudaMemset(ctx->d_queue_count, 0, 4 * sizeof(unsigned int)));
     ctx->retrace_min_cross = 3;
@@ -123,6 +127,8 @@ extern "C" int bhr_set_option(bhr_ctx* ctx, const char* key, double value) {
     if (!strcmp(key, "raymarch_mode")) { bhr_raymarch_mode_override = (int)value; return BHR_OK; }
     if (ctx && !strcmp(key, "retrace_min_cross")) { ctx->retrace_min_cross = (int)value; return BHR_OK; }
     if (ctx && !strcmp(key, "retrace_band")) { ctx->retrace_band = (float)value; return BHR_OK; }
+    if (ctx && !strcmp(key, "persistent")) { ctx->persistent = (int)value; return BHR_OK; }
+    if (ctx && !strcmp(key, "pblock_big")) { ctx->pblock_big = (int)value; return BHR_OK; }
     if (ctx) snprintf(ctx->err, sizeof(ctx->err), "unknown option %s", key);
     return BHR_ERR_INVALID;
 }

@@ -41,6 +41,11 @@ struct RayParams {
     int retrace_min_cross;
     float retrace_band;         // |b / b_crit - 1| below which a ray is traced by the strict integrator
     float inv_rcam3;            // 1 / |cam|^3
+    int* band;                  // persistent kernel: pixels of the ill-conditioned band (built beforehand)
+    unsigned int* band_count;
+    unsigned int* band_head;    // batches of 32 band rays claimed so far
+    unsigned int* tile_counter; // fast tiles claimed so far
+    int band_prequeued;
 };
 
 struct bhr_ctx {
@@ -58,7 +63,7 @@ struct bhr_ctx {
     uint8_t* final_u8;                 // (H, W, 3)
     uint8_t* cls; int* steps;
     unsigned long long* d_total_steps;
-    unsigned long long* retrace_queue; unsigned int* d_queue_count; int retrace_min_cross; unsigned int queue_serial; float retrace_band;
+    unsigned long long* retrace_queue; unsigned int* d_queue_count; int retrace_min_cross; unsigned int queue_serial; float retrace_band; int persistent, num_sms, pblock_big;
     double* d_flare_sums;              // {sum B, sum x*B, sum y*B}
 
     int bloom_R; float sigma_scale;

@@ -18,6 +18,8 @@ r = Renderer(W, H, synthetic_skybox(), synthetic_disk_texture(n_r, n_phi), **kw)
 r.set_option("raymarch_mode", mode); r.set_option("retrace_min_cross", retrace)
 band = float(os.environ.get("BAND", "0.02")) if retrace else 0.0
 r.set_option("retrace_band", band)
+r.set_option("persistent", int(os.environ.get("PERSISTENT", "1")))
+r.set_option("pblock_big", int(os.environ.get("BIG", "0")))
 for _ in range(4): r.render_device(pov, fov)
 r.synchronize()
 print(res, "mode", mode, "retrace", retrace, kw, r.last_stage_ms(), "steps", r.last_total_steps(), "retraced", r.last_retrace_count())
