@@ -5,11 +5,11 @@
 // host-side numpy composite `clip(img + disk + blur, 0, 1)` + transpose (render.py:3918-3923),
 // the numpy lens flare (render.py:3925-4028) and the truncating u8 conversion (render.py:4463).
 //
-// Layers are planar (3 x H x W).  Both passes keep a sliding window of weights and P running
-// outputs in registers so that every loaded sample feeds P FMAs:
-//   H pass: one warp per row segment of 32*P outputs, samples staged in shared memory;
-//   V pass: lanes along x (coalesced), P consecutive rows per thread, samples straight from
-//           L1/L2; the composite, the optional flare and the f32/u8 stores are fused in.
+// Layers are planar (3 x H x W).  Both passes keep a sliding window of weights and P = 10 running
+// outputs in registers so that every loaded sample feeds 10 FMAs:
+//   H pass: one warp per row segment of 320 outputs, samples staged transposed in shared memory;
+//   V pass: lanes along x, 10 consecutive rows per thread, a 32 x (80 + 2R) tile in shared memory;
+//   composite: streaming kernel, four pixels per thread, flare (float64) fused in.
 // Taps outside the image are skipped and the sum is renormalised by the in-bounds weight sum,
 // which is tabulated per x / per y in the reference's sequential f32 summation order.
 #include <math.h>
@@ -19,12 +19,17 @@
 
 namespace {
 
-constexpr int P_OUT = 8;   // outputs per thread
+constexpr int P_OUT = 10;   // outputs per thread: 32 * 10 = 320 divides every standard frame width
+
+__host__ __device__ constexpr int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
 // ---------------------------------------------------------------------------------------------
-// H pass.  block = 8 warps; warp w handles row (blockIdx.y * 8 + w), outputs x0 .. x0 + 255.
-// Shared row segment: s in [0, 256 + 2R) <-> x = x0 - R + s, stored at s + s / 32 (one pad word
-// per 32) so that the stride-8 lane access pattern is bank-conflict free.
+// H pass (one channel plane per blockIdx.z).  block = 8 warps; warp w blurs outputs
+// x0 .. x0 + 319 of row blockIdx.y * 8 + w.  Thread `lane` owns the 10 consecutive outputs
+// x0 + 10 lane + p.  The row segment (sample s <-> x = x0 - R + s) is staged in shared memory
+// TRANSPOSED: s lives at (s % 10) * pitch + s / 10, so that window position k = 10 j + kk of all
+// lanes reads the consecutive words kk * pitch + j + lane (no bank conflicts, no index math).
+// Each loaded sample feeds 10 FMAs through a sliding register window of weights.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) bloom_h_kernel(const float* __restrict__ src, float* __restrict__ dst,
                                                       int W, int row0, int row1, int R,
@@ -33,20 +38,20 @@ __global__ void __launch_bounds__(256) bloom_h_kernel(const float* __restrict__ 
     extern __shared__ float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ch = blockIdx.z;
-    const int nk = (2 * R + P_OUT + P_OUT - 1) / P_OUT * P_OUT;   // window positions, padded to P_OUT
-    const int seg = 32 * P_OUT - P_OUT + nk;                      // samples any lane may touch
-    const int seg_pad = seg + seg / 32 + 1;
-    float* wsh = smem;                                  // zero-padded weights of this channel
-    float* row = smem + wtab_stride + warp * seg_pad;
+    const int nk = round_up(2 * R + P_OUT, P_OUT);          // window positions, padded to P_OUT
+    const int seg = 31 * P_OUT + nk;                        // samples any lane may touch
+    const int pitch = (seg / P_OUT + 1) | 1;                // odd: spreads the staging stores over banks
+    float* wsh = smem;                                      // zero-padded weights of this channel
+    float* row = smem + wtab_stride + warp * (P_OUT * pitch);
     for (int k = threadIdx.x; k < wtab_stride; k += 256) wsh[k] = wtab[ch * wtab_stride + k];
     const int y = row0 + blockIdx.y * 8 + warp;
-    const int x0 = blockIdx.x * 256;
+    const int x0 = blockIdx.x * (32 * P_OUT);
     const bool row_ok = y < row1;
     if (row_ok) {
         const float* srow = src + ch * plane + (size_t)y * W;
         for (int s = lane; s < seg; s += 32) {
-            int x = x0 - R + s;
-            row[s + (s >> 5)] = (x >= 0 && x < W) ? __ldg(srow + x) : 0.0f;
+            const int x = x0 - R + s;
+            row[(s % P_OUT) * pitch + s / P_OUT] = (x >= 0 && x < W) ? __ldg(srow + x) : 0.0f;
         }
     }
     __syncthreads();
@@ -55,29 +60,32 @@ __global__ void __launch_bounds__(256) bloom_h_kernel(const float* __restrict__ 
     float acc[P_OUT], wr[P_OUT];
 #pragma unroll
     for (int p = 0; p < P_OUT; ++p) { acc[p] = 0.0f; wr[p] = 0.0f; }
-    const int base = lane * P_OUT;
-    for (int k0 = 0; k0 < nk; k0 += P_OUT) {
+    const float* rp = row + lane;
+    for (int k0 = 0; k0 < nk; k0 += P_OUT, ++rp) {
 #pragma unroll
         for (int kk = 0; kk < P_OUT; ++kk) {
-            const int k = k0 + kk;
-            const int s = base + k;
             // rotate the weight window: wr[p] = w[k - p]  (zero outside [0, 2R])
 #pragma unroll
             for (int p = P_OUT - 1; p > 0; --p) wr[p] = wr[p - 1];
-            wr[0] = wsh[k];
-            const float v = row[s + (s >> 5)];
+            wr[0] = wsh[k0 + kk];
+            const float v = rp[kk * pitch];
 #pragma unroll
             for (int p = 0; p < P_OUT; ++p) acc[p] = fmaf(v, wr[p], acc[p]);
         }
     }
+    // transpose the results through the (now free) row buffer for coalesced stores
+    __syncwarp();
+#pragma unroll
+    for (int p = 0; p < P_OUT; ++p) row[p * pitch + lane] = acc[p];
+    __syncwarp();
     float* drow = dst + ch * plane + (size_t)y * W;
     const float* ws = wsum_x + ch * W;
-#pragma unroll
-    for (int p = 0; p < P_OUT; ++p) {
-        int x = x0 + base + p;
+    for (int i = lane; i < 32 * P_OUT; i += 32) {
+        const int x = x0 + i;
         if (x < W) {
-            float wsum = ws[x];
-            drow[x] = wsum > 0.0f ? acc[p] / wsum : 0.0f;
+            const float wsum = ws[x];
+            const float a = row[(i % P_OUT) * pitch + i / P_OUT];
+            drow[x] = wsum > 0.0f ? a / wsum : 0.0f;
         }
     }
 }
@@ -96,53 +104,56 @@ __device__ __forceinline__ double np_mod(double a, double b) {   // numpy.mod fo
     return m;
 }
 
-// Every term is zero for most pixels; the squared-distance / slope pre-tests below skip the
-// sqrt / atan2 / exp of terms that cannot contribute (a skipped term adds exactly 0, as in numpy).
+// Every term is zero for most pixels; squared-distance / slope pre-tests skip the sqrt / atan2 /
+// exp of terms that cannot contribute (a skipped term adds exactly 0, as in numpy).  The streak
+// mask is a discontinuity and is decided in float64 exactly like the reference.
 __device__ void flare_pixel(const FlareParams& F, int x, int y, float fl[3]) {
     const double PI = 3.14159265358979323846;
     const double GUARD = 1.0 + 1e-9;
     fl[0] = fl[1] = fl[2] = 0.0f;
+    // Ghosts, rings and the hexagon are continuous functions of the pixel position: centres are
+    // formed in float64, the per-pixel distance algebra runs in float32 (error ~1e-6 of a term
+    // <= 1.5, far inside the 2/255 gate); the `flare` accumulation keeps numpy's f64-add/f32-store.
     const double gc[3] = {1.0, 0.9, 0.7};
+    const float inten = (float)F.intensity, fscale = (float)F.scale;
     for (int g = 0; g < 8; ++g) {
         double t = (g + 1) * 0.15;
         double gx = F.light_x + (F.scx - F.light_x) * t, gy = F.light_y + (F.scy - F.light_y) * t;
-        double size = (25 + g * 30) * F.scale;
-        double dx = x - gx, dy = y - gy;
-        double d2 = dx * dx + dy * dy;
-        if (d2 >= size * size * GUARD) continue;
-        double dist = sqrt(d2);
-        float alpha = 0.0f;
-        if (dist < size) { double u = 1 - dist / size; alpha = (float)(u * u * (1 - g * 0.08) * F.intensity); }
+        float size = (float)(25 + g * 30) * fscale;
+        float dx = (float)(x - gx), dy = (float)(y - gy);
+        float d2 = dx * dx + dy * dy;
+        if (d2 >= size * size) continue;
+        float u = 1.0f - sqrtf(d2) / size;
+        float alpha = u * u * (float)(1 - g * 0.08) * inten;
         for (int c = 0; c < 3; ++c) fl[c] = (float)((double)fl[c] + (double)alpha * gc[c]);
     }
     const double rc[3][3] = {{0.3, 0.4, 1.0}, {0.5, 0.5, 0.9}, {0.7, 0.5, 0.8}};
     for (int k = 0; k < 3; ++k) {
         double t = 0.35 + k * 0.15;
         double rx = F.light_x + (F.scx - F.light_x) * t, ry = F.light_y + (F.scy - F.light_y) * t;
-        double rr = (60 + k * 40) * F.scale, rw = (6 + k * 3) * F.scale;
-        double dx = x - rx, dy = y - ry;
-        double d2 = dx * dx + dy * dy;
-        double lo = rr - rw, hi = rr + rw;
-        if (d2 >= hi * hi * GUARD || (lo > 0 && d2 * GUARD <= lo * lo)) continue;
-        double dist = sqrt(d2);
-        double u = fmin(fmax(1 - fabs(dist - rr) / rw, 0.0), 1.0);
-        double ra = u * u * 0.5 * F.intensity * (1 - k * 0.25);
+        float rr = (float)(60 + k * 40) * fscale, rw = (float)(6 + k * 3) * fscale;
+        float dx = (float)(x - rx), dy = (float)(y - ry);
+        float d2 = dx * dx + dy * dy;
+        float lo = rr - rw, hi = rr + rw;
+        if (d2 >= hi * hi || (lo > 0.0f && d2 <= lo * lo)) continue;
+        float u = fminf(fmaxf(1.0f - fabsf(sqrtf(d2) - rr) / rw, 0.0f), 1.0f);
+        double ra = (double)(u * u * 0.5f * inten * (float)(1 - k * 0.25));
         for (int c = 0; c < 3; ++c) fl[c] = (float)((double)fl[c] + ra * rc[k][c]);
     }
     {
         const double hc[3] = {0.6, 0.7, 1.0};
         double hx = F.light_x + (F.scx - F.light_x) * 0.5, hy = F.light_y + (F.scy - F.light_y) * 0.5;
-        double hr = 100 * F.scale, hw = 15 * F.scale;
-        double dx = x - hx, dy = y - hy;
-        double d2 = dx * dx + dy * dy;
-        double lo = hr - hw, hi = hr + hw;
-        if (!(d2 >= hi * hi * GUARD || (lo > 0 && d2 * GUARD <= lo * lo))) {
-            double angle = atan2(dy, dx);
-            double dist = sqrt(d2);
-            double edge = fabs(np_mod(angle, PI / 3) - PI / 6);
-            double hf = fmin(fmax(1 - edge / 0.2, 0.0), 1.0);
-            double u = fmin(fmax(1 - fabs(dist - hr) / hw, 0.0), 1.0);
-            double ra = u * u * hf * 0.3 * F.intensity;
+        float hr = 100.0f * fscale, hw = 15.0f * fscale;
+        float dx = (float)(x - hx), dy = (float)(y - hy);
+        float d2 = dx * dx + dy * dy;
+        float lo = hr - hw, hi = hr + hw;
+        if (!(d2 >= hi * hi || (lo > 0.0f && d2 <= lo * lo))) {
+            float angle = atan2f(dy, dx);
+            float m = fmodf(angle, 1.0471976f);
+            if (m < 0.0f) m += 1.0471976f;
+            float hf = fminf(fmaxf(1.0f - fabsf(m - 0.5235988f) / 0.2f, 0.0f), 1.0f);
+            float u = fminf(fmaxf(1.0f - fabsf(sqrtf(d2) - hr) / hw, 0.0f), 1.0f);
+            double ra = (double)(u * u * hf * 0.3f * inten);
             for (int c = 0; c < 3; ++c) fl[c] = (float)((double)fl[c] + ra * hc[c]);
         }
     }
@@ -168,95 +179,130 @@ __device__ void flare_pixel(const FlareParams& F, int x, int y, float fl[3]) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// V pass + composite.  block = 32 (x) x 8 (row groups) threads, tile = 32 columns x 64 rows.
-// Per channel the block stages the (64 + 2R) x 32 samples it needs in shared memory (coalesced
-// rows, zero outside the image; 2.2x re-read instead of 10x), then each thread slides its
-// 8-output window down the column.  Composite, flare and the f32 / u8 stores are fused in.
+// V pass (one channel plane per blockIdx.z).  block = 32 (x) x 8 (row groups) threads, tile =
+// 32 columns x 80 rows.  The (80 + 2R) x 32 samples are staged in shared memory (coalesced rows,
+// zero outside the image); each thread slides its 10-output window down its column.
 // ---------------------------------------------------------------------------------------------
-constexpr int V_TILE_ROWS = 8 * P_OUT;   // 64
+constexpr int V_TILE_ROWS = 8 * P_OUT;
 
-template <bool BLOOM>
-__global__ void __launch_bounds__(256) bloom_v_composite_kernel(
-    const float* __restrict__ hblur, const float* __restrict__ bg, const float* __restrict__ disk,
-    float* __restrict__ blur_out, float* __restrict__ final_f32, uint8_t* __restrict__ final_u8,
-    int W, int H, int row0, int row1, int R, const float* __restrict__ wtab, int wtab_stride,
-    const float* __restrict__ wsum_y, size_t plane, FlareParams F) {
+__global__ void __launch_bounds__(256) bloom_v_kernel(const float* __restrict__ hblur, float* __restrict__ blur,
+                                                      int W, int H, int row0, int row1, int R,
+                                                      const float* __restrict__ wtab, int wtab_stride,
+                                                      const float* __restrict__ wsum_y, size_t plane) {
     extern __shared__ float vsm[];
-    const int nk = (2 * R + P_OUT + P_OUT - 1) / P_OUT * P_OUT;    // window positions, padded
-    const int tile_rows = V_TILE_ROWS - P_OUT + nk;                // rows any thread may touch
-    float* wsh = vsm;                                              // 3 x wtab_stride weights
-    float* tile = vsm + 3 * wtab_stride;                           // tile_rows x 32
+    const int ch = blockIdx.z;
+    const int nk = round_up(2 * R + P_OUT, P_OUT);
+    const int tile_rows = V_TILE_ROWS - P_OUT + nk;
+    float* wsh = vsm;
+    float* tile = vsm + wtab_stride;
     const int tid = threadIdx.y * 32 + threadIdx.x;
-    if (BLOOM)
-        for (int k = tid; k < 3 * wtab_stride; k += 256) wsh[k] = wtab[k];
+    for (int k = tid; k < wtab_stride; k += 256) wsh[k] = wtab[ch * wtab_stride + k];
     const int x = blockIdx.x * 32 + threadIdx.x;
-    const int ty0 = row0 + blockIdx.y * V_TILE_ROWS;               // first output row of the tile
-    const int y0 = ty0 + threadIdx.y * P_OUT;                      // first output row of this thread
+    const int ty0 = row0 + blockIdx.y * V_TILE_ROWS;
     const bool col_ok = x < W;
-
-    float val[3][P_OUT];
+    const float* src = hblur + ch * plane;
+    for (int r = threadIdx.y; r < tile_rows; r += 8) {
+        const int y = ty0 - R + r;
+        tile[r * 32 + threadIdx.x] = (col_ok && y >= 0 && y < H) ? __ldg(src + (size_t)y * W + x) : 0.0f;
+    }
+    __syncthreads();
+    float acc[P_OUT], wr[P_OUT];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        float acc[P_OUT], wr[P_OUT];
+    for (int p = 0; p < P_OUT; ++p) { acc[p] = 0.0f; wr[p] = 0.0f; }
+    const float* colp = tile + threadIdx.y * P_OUT * 32 + threadIdx.x;
+    for (int k0 = 0; k0 < nk; k0 += P_OUT, colp += P_OUT * 32) {
 #pragma unroll
-        for (int p = 0; p < P_OUT; ++p) { acc[p] = 0.0f; wr[p] = 0.0f; }
-        if (BLOOM) {
-            __syncthreads();                                       // previous channel's tile is consumed
-            const float* src = hblur + c * plane;
-            for (int r = threadIdx.y; r < tile_rows; r += 8) {
-                const int y = ty0 - R + r;
-                tile[r * 32 + threadIdx.x] = (col_ok && y >= 0 && y < H) ? __ldg(src + (size_t)y * W + x) : 0.0f;
-            }
-            __syncthreads();
-            const float* wc = wsh + c * wtab_stride;
-            const float* colp = tile + threadIdx.y * P_OUT * 32 + threadIdx.x;
-            for (int k0 = 0; k0 < nk; k0 += P_OUT) {
+        for (int kk = 0; kk < P_OUT; ++kk) {
 #pragma unroll
-                for (int kk = 0; kk < P_OUT; ++kk) {
-                    const int k = k0 + kk;
+            for (int p = P_OUT - 1; p > 0; --p) wr[p] = wr[p - 1];
+            wr[0] = wsh[k0 + kk];
+            const float v = colp[kk * 32];
 #pragma unroll
-                    for (int p = P_OUT - 1; p > 0; --p) wr[p] = wr[p - 1];
-                    wr[0] = wc[k];
-                    const float v = colp[k * 32];
-#pragma unroll
-                    for (int p = 0; p < P_OUT; ++p) acc[p] = fmaf(v, wr[p], acc[p]);
-                }
-            }
-        }
-#pragma unroll
-        for (int p = 0; p < P_OUT; ++p) {
-            const int y = y0 + p;
-            float b = 0.0f;
-            val[c][p] = 0.0f;
-            if (col_ok && y < row1) {
-                const size_t o = c * plane + (size_t)y * W + x;
-                float v = bg[o] + disk[o];
-                if (BLOOM) {
-                    float wsum = wsum_y[c * H + y];
-                    b = wsum > 0.0f ? acc[p] / wsum : 0.0f;
-                    if (blur_out) blur_out[o] = b;
-                    v = v + b;
-                }
-                val[c][p] = fminf(fmaxf(v, 0.0f), 1.0f);
-            }
+            for (int p = 0; p < P_OUT; ++p) acc[p] = fmaf(v, wr[p], acc[p]);
         }
     }
     if (!col_ok) return;
+    const int y0 = ty0 + threadIdx.y * P_OUT;
+    float* dst = blur + ch * plane;
 #pragma unroll
     for (int p = 0; p < P_OUT; ++p) {
         const int y = y0 + p;
-        if (y >= row1) break;
-        float r = val[0][p], g = val[1][p], b = val[2][p];
-        if (F.enabled) {
-            float fl[3];
-            flare_pixel(F, x, y, fl);
-            r = fminf(fmaxf(r + fl[0], 0.0f), 1.0f);
-            g = fminf(fmaxf(g + fl[1], 0.0f), 1.0f);
-            b = fminf(fmaxf(b + fl[2], 0.0f), 1.0f);
+        if (y < row1) {
+            const float wsum = wsum_y[ch * H + y];
+            dst[(size_t)y * W + x] = wsum > 0.0f ? acc[p] / wsum : 0.0f;
         }
-        const size_t o = ((size_t)y * W + x) * 3;
-        final_f32[o] = r; final_f32[o + 1] = g; final_f32[o + 2] = b;
-        final_u8[o] = (uint8_t)(r * 255.0f); final_u8[o + 1] = (uint8_t)(g * 255.0f); final_u8[o + 2] = (uint8_t)(b * 255.0f);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Composite: final = clip(bg + disk [+ blur], 0, 1) [+ flare], written as (H, W, 3) f32 and u8
+// (render.py:3912-3923, 4463).  Four pixels per thread: float4 plane loads, 3 x float4 + 3 x u32
+// stores when the width allows it.
+// ---------------------------------------------------------------------------------------------
+template <bool BLOOM, int VEC, bool FLARE>
+__global__ void __launch_bounds__(256) composite_kernel(const float* __restrict__ bg, const float* __restrict__ disk,
+                                                        const float* __restrict__ blur, float* __restrict__ final_f32,
+                                                        uint8_t* __restrict__ final_u8, int W, int row0, int row1,
+                                                        size_t plane, FlareParams F) {
+    const int groups_per_row = (W + VEC - 1) / VEC;
+    const size_t n = (size_t)(row1 - row0) * groups_per_row;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int y = row0 + (int)(i / groups_per_row), x = (int)(i % groups_per_row) * VEC;
+        const size_t o = (size_t)y * W + x;
+        float v[3][VEC];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float a[VEC], d[VEC], b[VEC];
+            if (VEC == 4) {
+                const float4 a4 = *reinterpret_cast<const float4*>(bg + c * plane + o);
+                const float4 d4 = *reinterpret_cast<const float4*>(disk + c * plane + o);
+                a[0] = a4.x; a[1] = a4.y; a[2] = a4.z; a[3] = a4.w;
+                d[0] = d4.x; d[1] = d4.y; d[2] = d4.z; d[3] = d4.w;
+                if (BLOOM) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(blur + c * plane + o);
+                    b[0] = b4.x; b[1] = b4.y; b[2] = b4.z; b[3] = b4.w;
+                }
+            } else {
+                a[0] = bg[c * plane + o]; d[0] = disk[c * plane + o];
+                if (BLOOM) b[0] = blur[c * plane + o];
+            }
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                float t = a[j] + d[j];
+                if (BLOOM) t = t + b[j];
+                v[c][j] = fminf(fmaxf(t, 0.0f), 1.0f);
+            }
+        }
+        if (FLARE) {
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                float fl[3];
+                flare_pixel(F, x + j, y, fl);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) v[c][j] = fminf(fmaxf(v[c][j] + fl[c], 0.0f), 1.0f);
+            }
+        }
+        if (VEC == 4) {
+            float4* of = reinterpret_cast<float4*>(final_f32 + o * 3);
+            of[0] = make_float4(v[0][0], v[1][0], v[2][0], v[0][1]);
+            of[1] = make_float4(v[1][1], v[2][1], v[0][2], v[1][2]);
+            of[2] = make_float4(v[2][2], v[0][3], v[1][3], v[2][3]);
+            unsigned char q[12];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) q[j * 3 + c] = (unsigned char)(v[c][j] * 255.0f);
+            uint32_t* ou = reinterpret_cast<uint32_t*>(final_u8 + o * 3);
+#pragma unroll
+            for (int w = 0; w < 3; ++w)
+                ou[w] = (uint32_t)q[4 * w] | ((uint32_t)q[4 * w + 1] << 8) | ((uint32_t)q[4 * w + 2] << 16) | ((uint32_t)q[4 * w + 3] << 24);
+        } else {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                final_f32[o * 3 + c] = v[c][0];
+                final_u8[o * 3 + c] = (unsigned char)(v[c][0] * 255.0f);
+            }
+        }
     }
 }
 
@@ -296,8 +342,7 @@ int bhr_setup_bloom_tables(bhr_ctx* ctx) {
     const int R = (int)(W * 0.02);                          // render.py:3914
     const float sigma_scale = (float)((W / 640.0) * (W / 640.0));   // render.py:3915 (f64 -> f32 kernel arg)
     ctx->bloom_R = R; ctx->sigma_scale = sigma_scale;
-    const int taps = 2 * R + 1;
-    const int stride = (taps + 2 * P_OUT) / P_OUT * P_OUT;  // zero padded past the last tap
+    const int stride = round_up(2 * R + P_OUT, P_OUT) + P_OUT;   // zero padded past the last tap
     ctx->wtab_stride = stride;
     float* wt = (float*)calloc((size_t)3 * stride, sizeof(float));
     float* wx = (float*)malloc((size_t)3 * W * sizeof(float));
@@ -334,10 +379,10 @@ int bhr_setup_bloom_tables(bhr_ctx* ctx) {
 int bhr_launch_bloom_h(bhr_ctx* ctx, int row0, int row1) {
     if (row1 <= row0) return BHR_OK;
     const int R = ctx->bloom_R;
-    const int nk = (2 * R + P_OUT + P_OUT - 1) / P_OUT * P_OUT;
-    const int seg = 32 * P_OUT - P_OUT + nk, seg_pad = seg + seg / 32 + 1;
-    size_t smem = (size_t)(ctx->wtab_stride + 8 * seg_pad) * sizeof(float);
-    dim3 grid(bhr_div_up(ctx->W, 256), bhr_div_up(row1 - row0, 8), 3);
+    const int nk = round_up(2 * R + P_OUT, P_OUT);
+    const int seg = 31 * P_OUT + nk, pitch = (seg / P_OUT + 1) | 1;
+    size_t smem = (size_t)(ctx->wtab_stride + 8 * P_OUT * pitch) * sizeof(float);
+    dim3 grid(bhr_div_up(ctx->W, 32 * P_OUT), bhr_div_up(row1 - row0, 8), 3);
     bloom_h_kernel<<<grid, 256, smem, ctx->stream>>>(ctx->disk, ctx->hblur, ctx->W, row0, row1, R, ctx->d_wtab,
                                                      ctx->wtab_stride, ctx->d_wsum_x, (size_t)ctx->W * ctx->H);
     BHR_CUDA(ctx, cudaGetLastError());
@@ -375,22 +420,30 @@ int bhr_launch_bloom_v_composite(bhr_ctx* ctx, uint32_t flags, int row0, int row
             F.streak_len = (double)(W < H ? W : H) * 0.4;
         }
     }
-    dim3 block(32, 8);
-    dim3 grid(bhr_div_up(W, 32), bhr_div_up(row1 - row0, 8 * P_OUT));
     const size_t plane = (size_t)W * H;
-    if (flags & BHR_SKIP_BLOOM) {
-        bloom_v_composite_kernel<false><<<grid, block, 0, ctx->stream>>>(
-            ctx->hblur, ctx->bg, ctx->disk, nullptr, ctx->final_f32, ctx->final_u8, W, H, row0, row1, ctx->bloom_R,
-            ctx->d_wtab, ctx->wtab_stride, ctx->d_wsum_y, plane, F);
-    } else {
-        const int nk = (2 * ctx->bloom_R + P_OUT + P_OUT - 1) / P_OUT * P_OUT;
-        size_t smem = ((size_t)3 * ctx->wtab_stride + (size_t)(V_TILE_ROWS - P_OUT + nk) * 32) * sizeof(float);
+    const bool bloom = !(flags & BHR_SKIP_BLOOM);
+    if (bloom) {
+        const int nk = round_up(2 * ctx->bloom_R + P_OUT, P_OUT);
+        size_t smem = ((size_t)ctx->wtab_stride + (size_t)(V_TILE_ROWS - P_OUT + nk) * 32) * sizeof(float);
         if (smem > 48 * 1024)
-            BHR_CUDA(ctx, cudaFuncSetAttribute(bloom_v_composite_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        bloom_v_composite_kernel<true><<<grid, block, smem, ctx->stream>>>(
-            ctx->hblur, ctx->bg, ctx->disk, ctx->blur, ctx->final_f32, ctx->final_u8, W, H, row0, row1, ctx->bloom_R,
-            ctx->d_wtab, ctx->wtab_stride, ctx->d_wsum_y, plane, F);
+            BHR_CUDA(ctx, cudaFuncSetAttribute(bloom_v_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 block(32, 8), grid(bhr_div_up(W, 32), bhr_div_up(row1 - row0, V_TILE_ROWS), 3);
+        bloom_v_kernel<<<grid, block, smem, ctx->stream>>>(ctx->hblur, ctx->blur, W, H, row0, row1, ctx->bloom_R,
+                                                          ctx->d_wtab, ctx->wtab_stride, ctx->d_wsum_y, plane);
+        BHR_CUDA(ctx, cudaGetLastError());
     }
+    const int cgrid = 148 * 8;
+#define BHR_COMPOSITE(B, V, FL) composite_kernel<B, V, FL><<<cgrid, 256, 0, ctx->stream>>>( \
+        ctx->bg, ctx->disk, ctx->blur, ctx->final_f32, ctx->final_u8, W, row0, row1, plane, F)
+    const bool vec = (W % 4 == 0), fl = F.enabled != 0;
+    if (vec) {
+        if (bloom) { if (fl) BHR_COMPOSITE(true, 4, true); else BHR_COMPOSITE(true, 4, false); }
+        else { if (fl) BHR_COMPOSITE(false, 4, true); else BHR_COMPOSITE(false, 4, false); }
+    } else {
+        if (bloom) { if (fl) BHR_COMPOSITE(true, 1, true); else BHR_COMPOSITE(true, 1, false); }
+        else { if (fl) BHR_COMPOSITE(false, 1, true); else BHR_COMPOSITE(false, 1, false); }
+    }
+#undef BHR_COMPOSITE
     BHR_CUDA(ctx, cudaGetLastError());
     return BHR_OK;
 }

@@ -225,6 +225,8 @@ class EntityFactory:
         self.rng = np.random.default_rng(seed)
         self.entities: List[EntityInstance] = []
         self._spawn_debt = 0.0
+        self._version = 0          # bumped whenever the population changes (SoA cache key)
+        self._soa = None
         self.entity_type = entity_type
         if entity_type not in _DRAW:
             raise ValueError(f"unknown entity_type {entity_type!r}")
@@ -256,9 +258,30 @@ class EntityFactory:
                 stagger = (e.fade_in + e.lifetime) * (i / n)
             e.birth_time = now - stagger
             self.entities.append(e)
+        self._version += 1
 
     def tick(self, now, dt):
-        self.entities = [e for e in self.entities if not e.is_dead(now)]
+        before = len(self.entities)
+        if self.entity_type == "filament":
+            # inlined EntityInstance.is_dead (same arithmetic, same math.exp), 200 per frame
+            exp, thr, tmax = math.exp, FILAMENT_DEATH_THRESHOLD, FILAMENT_MAX_LIFETIME
+            keep = []
+            for e in self.entities:
+                age = now - e.birth_time
+                if age >= tmax:
+                    continue
+                if age >= 0:
+                    s0 = max(e.blob_sigma_phi0, 1e-6)
+                    cool = exp(-age / e.tau_cool) if e.tau_cool > 0 else 1.0
+                    if (s0 / (s0 + e.alpha_shear * age)) * cool < thr:
+                        continue
+                keep.append(e)
+            self.entities = keep
+        else:
+            self.entities = [e for e in self.entities
+                             if now - e.birth_time < e.fade_in + e.lifetime + e.fade_out]
+        if len(self.entities) != before:
+            self._version += 1
         deficit = self.target_count - len(self.entities)
         if deficit <= 0:
             return
@@ -268,6 +291,8 @@ class EntityFactory:
         self._spawn_debt -= n_spawn
         for _ in range(n_spawn):
             self.entities.append(self._spawn_one(now))
+        if n_spawn:
+            self._version += 1
 
     @property
     def alive_entities(self):
@@ -338,6 +363,82 @@ def pack_entities(factories, now, n_r):
                 ent.p[i] = v
             out.append(ent)
     return out
+
+
+ENTITY_DTYPE = np.dtype([("kind", "<i4"), ("row_begin", "<i4"), ("row_end", "<i4"), ("_pad", "<i4"),
+                         ("age", "<f8"), ("scale", "<f8"), ("p", "<f8", (8,))])
+assert ENTITY_DTYPE.itemsize == 96
+
+
+def _factory_soa(f, n_r):
+    """Static per-entity columns of a factory, rebuilt only when its population changes."""
+    key = (f._version, len(f.entities), n_r)
+    if f._soa is not None and f._soa[0] == key:
+        return f._soa[1]
+    ents = f.entities
+    n = len(ents)
+    col = dict(birth=np.array([e.birth_time for e in ents], dtype=np.float64).reshape(n),
+               r0=np.array([max(int(e.q["rows"][0]), 0) for e in ents], dtype=np.int32).reshape(n),
+               r1=np.array([min(int(e.q["rows"][1]), n_r) for e in ents], dtype=np.int32).reshape(n))
+    if f.entity_type == "filament":
+        for name in ("source_phi", "alpha_shear", "tau_cool", "blob_base_r", "blob_sigma_r",
+                     "blob_sigma_phi0", "blob_peak_density", "blob_peak_temp"):
+            col[name] = np.array([getattr(e, name) for e in ents], dtype=np.float64).reshape(n)
+    else:
+        names = (("phi0", "r0", "phi_width", "r_width", "intensity") if f.entity_type == "hotspot"
+                 else ("phi0", "r0", "phi_width", "r_length", "intensity", "delta_T"))
+        col["params"] = np.array([[e.q[k] for k in names] for e in ents], dtype=np.float64).reshape(n, len(names))
+        col["fade_in"] = np.array([e.fade_in for e in ents], dtype=np.float64).reshape(n)
+        col["life"] = np.array([e.lifetime for e in ents], dtype=np.float64).reshape(n)
+        col["fade_out"] = np.array([e.fade_out for e in ents], dtype=np.float64).reshape(n)
+    f._soa = (key, col)
+    return col
+
+
+def pack_entities_array(factories, now, n_r):
+    """Vectorised `pack_entities`: a numpy array with bhr_entity's layout.  Same formulas in
+    float64 (numpy's exp instead of math.exp: <= 1 ulp of a double on the scale factors)."""
+    parts = []
+    for key in ("filament", "rt_spike", "hotspot"):
+        f = factories.get(key)
+        if f is None or not f.entities:
+            continue
+        c = _factory_soa(f, n_r)
+        age = now - c["birth"]
+        if f.entity_type == "filament":
+            s0 = np.maximum(c["blob_sigma_phi0"], 1e-6)
+            sigma_t = s0 + c["alpha_shear"] * age
+            cool = np.where(c["tau_cool"] > 0, np.exp(-age / np.where(c["tau_cool"] > 0, c["tau_cool"], 1.0)), 1.0)
+            alive = (s0 / sigma_t) * cool >= FILAMENT_DEATH_THRESHOLD
+            birth = np.minimum(age / FILAMENT_BIRTH_FADE_DUR, 1.0)
+            sigma_r = np.maximum(c["blob_sigma_r"], 1e-6)
+            out = np.zeros(len(age), dtype=ENTITY_DTYPE)
+            out["kind"] = 0
+            out["scale"] = birth * cool
+            out["p"][:, 0] = c["source_phi"]
+            out["p"][:, 1] = c["blob_base_r"]
+            out["p"][:, 2] = 0.5 / (sigma_r * sigma_r)
+            out["p"][:, 3] = 0.5 / (sigma_t * sigma_t)
+            out["p"][:, 4] = c["blob_peak_density"] * s0 / sigma_t * birth * cool
+            out["p"][:, 5] = c["blob_peak_temp"] * s0 / sigma_t * birth * cool
+        else:
+            fin, life, fout = c["fade_in"], c["life"], c["fade_out"]
+            rest = age - fin
+            with np.errstate(divide="ignore", invalid="ignore"):
+                ramp_in = np.where(fin > 0, age / np.where(fin > 0, fin, 1.0), 1.0)
+                ramp_out = np.where(fout > 0, 1.0 - (rest - life) / np.where(fout > 0, fout, 1.0), 0.0)
+            alpha = np.where(age < 0, 0.0, np.where(age < fin, ramp_in, np.where(
+                rest < life, 1.0, np.where(rest - life < fout, ramp_out, 0.0))))
+            alive = alpha > 0
+            out = np.zeros(len(age), dtype=ENTITY_DTYPE)
+            out["kind"] = KIND[f.entity_type]
+            out["scale"] = alpha
+            out["p"][:, :c["params"].shape[1]] = c["params"]
+        out["row_begin"], out["row_end"], out["age"] = c["r0"], c["r1"], age
+        parts.append(out[alive])
+    if not parts:
+        return np.zeros(0, dtype=ENTITY_DTYPE)
+    return np.ascontiguousarray(np.concatenate(parts))
 
 
 def init_lifecycle_system(renderer, n_r, n_phi, seed=42):

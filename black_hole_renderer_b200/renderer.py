@@ -299,11 +299,11 @@ class Renderer:
 
     def accumulate_entity_layer(self, factories, now):
         """Sum every alive entity into comp[5:11] on the device (render.py:3564-3653)."""
-        from .lifecycle import pack_entities
+        from .lifecycle import pack_entities_array
         assert self._bg_ready, "Must call init_background_layer() first"
-        ents = pack_entities(factories, now, self._bg_n_r)
-        arr = (L.BhrEntity * max(len(ents), 1))(*ents)
-        self._check(self._lib.bhr_accumulate_entities(self._ctx, arr, len(ents)))
+        ents = pack_entities_array(factories, now, self._bg_n_r)
+        ptr = ents.ctypes.data_as(C.POINTER(L.BhrEntity)) if len(ents) else None
+        self._check(self._lib.bhr_accumulate_entities(self._ctx, ptr, len(ents)))
 
     def recompute_interactive_stats(self):
         """Normalisation statistics from the current component field (render.py:3655-3712):
