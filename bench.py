@@ -128,7 +128,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--resolution", default="fhd", choices=list(RES))
-    ap.add_argument("--mode", default=None, help="raymarch mode override: scalar | pair | strict")
+    ap.add_argument("--mode", default=None, help="raymarch mode override: fast | strict")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -154,7 +154,7 @@ def main():
     sky, n_r, n_phi = scene_inputs(W, H)
     r = Renderer(W, H, sky, np.zeros((n_r, n_phi, 4), np.float32), cuda_device=local)
     if args.mode:
-        r.set_option("raymarch_mode", {"scalar": 0, "pair": 1, "strict": 2}[args.mode])
+        r.set_option("raymarch_mode", {"fast": 0, "strict": 2}[args.mode])
     stream = torch.cuda.Stream()          # a real (non-legacy) stream: the kernels and the timing events share it
     torch.cuda.set_stream(stream)
     r.set_stream(stream.cuda_stream)

@@ -87,8 +87,8 @@ int bhr_set_stream(bhr_ctx* ctx, void* cuda_stream); /* NULL = the context's own
 int bhr_synchronize(bhr_ctx* ctx);
 int bhr_set_lens_flare(bhr_ctx* ctx, int enabled);  /* renderer.lens_flare attribute */
 int bhr_version(void);
-/* tuning knobs: "raymarch_mode" = 0 scalar FFMA (default), 1 packed FFMA2 (two rays per thread),
- * 2 strict (reference operation order, exactly rounded; ~2.5x slower); "retrace_band" = eps: rays
+/* tuning knobs: "raymarch_mode" = 0 fast integrator (default; re-associated RK4, packed FFMA2),
+ * 2 strict (reference operation order, exactly rounded; ~3x slower); "retrace_band" = eps: rays
  * whose impact parameter is within eps of the critical one (photon-ring rays, chaotic) are traced
  * by the strict integrator (default 0.02, 0 = off); "retrace_min_cross" = n: safety net, rays with
  * >= n disk-plane crossings are re-traced too (default 3, 0 = off); "persistent" = 1 (default):

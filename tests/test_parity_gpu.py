@@ -19,7 +19,7 @@ from util import GOLDEN, RESOLUTIONS, parity_report, synthetic_disk_texture, syn
 pytestmark = pytest.mark.gpu
 
 CASES = ["raymarch_default", "raymarch_aa_tilt_flare", "raymarch_e2e_like", "raymarch_offaxis_fine"]
-MODES = {"scalar": 0, "pair": 1, "strict": 2}
+MODES = {"fast": 0, "strict": 2}
 
 
 def _renderer_for(d, mode):
@@ -50,7 +50,7 @@ def test_strict_mode_matches_reference_goldens(name):
         assert np.abs(img - d["final_skip_diff"]).max() < 2e-5
 
 
-@pytest.mark.parametrize("mode", ["scalar", "pair"])
+@pytest.mark.parametrize("mode", ["fast"])
 @pytest.mark.parametrize("name", CASES)
 def test_fast_modes_match_reference_goldens(name, mode):
     d = np.load(os.path.join(GOLDEN, name + ".npz"))
@@ -94,7 +94,7 @@ def _check_gate(r, ref, pov, fov, max_class_frac=1e-4):
     return rep, steps
 
 
-@pytest.mark.parametrize("mode", ["scalar", "pair", "strict"])
+@pytest.mark.parametrize("mode", ["fast", "strict"])
 def test_config1_sd_default_scene(mode):
     """BASELINE.json configs[0]: -r sd, pov 6 0 0.5, fov 90, step 0.1, r_max 10."""
     kw = {}

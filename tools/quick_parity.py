@@ -43,11 +43,11 @@ def scene(res, mode, **kw):
     print("      parity", rep, "steps equal frac", float((steps == ref["steps"]).mean()))
 
 if __name__ == "__main__":
-    for mode in (2, 0, 1):
+    for mode in (2, 0):
         for n in ["raymarch_default", "raymarch_aa_tilt_flare", "raymarch_e2e_like", "raymarch_offaxis_fine"]:
             golden_case(n, mode)
-    for mode in (2, 0, 1):
+    for mode in (2, 0):
         scene("sd", mode)
     scene("sd", 0, anti_alias="lod_radius", disk_tilt=20.0, lens_flare=True)
-    for mode in (0, 1):
+    for mode in (0,):
         scene("fhd", mode)
