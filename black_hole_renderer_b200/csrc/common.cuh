@@ -18,6 +18,8 @@ struct RayParams {
     float pw, ph;
     float r_esc, r_esc2;
     float h_base, r_in, r_out, t_offset;
+    float inv_span, inv_span_clamped;   // 1 / (r_out - r_in), 1 / max(r_out - r_in, 1e-3)
+    float grav_num;             // sqrt(max(1 - 1 / max(|cam|, 1.001), 1e-6)), render.py:2480
     float tilt_rad, tan_t, sin_t, cos_t;
     int max_iter;
     float max_affine;
