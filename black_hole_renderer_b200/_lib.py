@@ -71,6 +71,7 @@ SIGNATURES = {
     "bhr_compose_texture": (C.c_int, [_P, C.c_float, C.c_int, C.c_float]),
     "bhr_eval_noise": (C.c_int, [_P, _FP, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, _FP]),
     "bhr_measure_fp32_peak": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),
+    "bhr_selftest_div6": (C.c_int, [C.c_int, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]),
 }
 
 _lib = None

@@ -166,6 +166,11 @@ int bhr_eval_noise(bhr_ctx* ctx, const float* coords, int n, int mode, int octav
 /* FP32 FMA throughput microbenchmark (TFLOP/s): mode 0 scalar FFMA, 1 packed FFMA2 */
 int bhr_measure_fp32_peak(int device, int mode, double* tflops);
 
+/* self-test of the strict integrator's three-instruction x / 6: compares it with the IEEE division
+ * on all 2^32 float bit patterns and returns the number of mismatches among the inputs whose
+ * quotient is a normal number or zero (expected 0), and among all inputs */
+int bhr_selftest_div6(int device, unsigned long long* mismatches_normal, unsigned long long* mismatches_all);
+
 #ifdef __cplusplus
 }
 #endif

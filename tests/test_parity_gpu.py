@@ -204,3 +204,17 @@ def test_update_disk_texture_and_errors():
         r.update_disk_texture(np.zeros((tex.shape[0] // 2, tex.shape[1], 4), np.float32))
     mips = r.disk_mips_field.to_numpy()
     assert np.array_equal(mips, O.build_mips(tex, 5, numpy_order=True))
+
+
+def test_strict_div6_is_the_ieee_division_on_every_float():
+    """The strict integrator divides the RK4 sums by 6 with a three-instruction sequence; it must
+    be bit-identical to the IEEE division (exhaustive over all 2^32 inputs)."""
+    import ctypes as C
+    from black_hole_renderer_b200 import _lib as L
+    lib = L.load()
+    normal, total = C.c_ulonglong(123), C.c_ulonglong(123)
+    assert lib.bhr_selftest_div6(0, C.byref(normal), C.byref(total)) == 0
+    assert normal.value == 0, (normal.value, total.value)
+    # the only inputs that may differ are those whose quotient is subnormal (|x| < 6 * 2^-126);
+    # positions / directions of a ray never get there
+    assert total.value < 2 * 6 * 2 ** 23 + 16

@@ -12,7 +12,7 @@ def run(res, pov, fov, **kw):
     W, H = RESOLUTIONS[res] if isinstance(res, str) else res
     n_phi, n_r = O.disk_texture_resolution(W, H, pov, fov, kw.get("r_disk_inner", 2.0), kw.get("r_disk_outer", 15.0))
     sky = synthetic_skybox(); tex = synthetic_disk_texture(n_r, n_phi)
-    r = Renderer(W, H, sky, tex, **kw); r.set_option("raymarch_mode", 0); r.set_option("retrace_min_cross", 0)
+    r = Renderer(W, H, sky, tex, **kw); r.set_option("raymarch_mode", 0); r.set_option("retrace_min_cross", int(os.environ.get("MINCROSS", "0"))); r.set_option("retrace_band", float(os.environ.get("BAND", "0.02")))
     img = r.render(pov, fov, aux=True, skip_bloom=True); cls, steps = r.last_aux()
     okw = dict(step_size=kw.get("step_size", 0.1), r_max=kw.get("r_max", 10.0), r_inner=kw.get("r_disk_inner", 2.0),
                r_outer=kw.get("r_disk_outer", 15.0), disk_tilt=kw.get("disk_tilt", 0.0))
@@ -24,15 +24,23 @@ def run(res, pov, fov, **kw):
     dirs = fwd[None,None,:] + xs[None,:,None]*right[None,None,:] + ys[:,None,None]*up[None,None,:]
     dirs /= np.linalg.norm(dirs, axis=-1, keepdims=True)
     b = np.linalg.norm(np.cross(dirs, p[None,None,:]), axis=-1)
-    eps = b/BC - 1
+    rc = np.linalg.norm(p)
+    eps = b/np.sqrt(np.maximum(1 - b*b/rc**3, 1e-6))/BC - 1     # impact parameter at infinity, as in the kernel
     nc = cls >> 5
     steps_diff = steps != ref['steps']
     clsd = (cls & 31) != (ref['term'] | (np.minimum(ref['nhits'],7) << 2))
-    print(f"{res} pov={pov} fov={fov} {kw}: bad(d>1)={int((d>1).sum())} bad(d>2)={int((d>2).sum())} clsdiff={int(clsd.sum())} stepdiff={int(steps_diff.sum())}")
+    same = ~steps_diff & ~clsd
+    print(f"{res} pov={pov} fov={fov} {kw}: bad(d>1)={int((d>1).sum())} bad(d>2)={int((d>2).sum())} clsdiff={int(clsd.sum())} stepdiff={int(steps_diff.sum())}  | same steps+class: d>1 {int((d>1)[same].sum())} d>2 {int((d>2)[same].sum())} retraced {r.last_retrace_count()}")
+    if os.environ.get("DETAIL"):
+        bg = r.image_field.to_numpy().transpose(1,0,2); dk = r.disk_layer_field.to_numpy().transpose(1,0,2)
+        ys_, xs_ = np.nonzero(d > 1)
+        for y, x in list(zip(ys_, xs_))[:12]:
+            print(f"     px ({x},{y}) d={d[y,x]} eps={eps[y,x]:.4f} cls gpu {cls[y,x]&31} ref {ref['term'][y,x] | (min(ref['nhits'][y,x],7)<<2)} steps gpu {steps[y,x]} ref {ref['steps'][y,x]} ncross {nc[y,x]}"
+                  f"\n        gpu bg {bg[y,x]} disk {dk[y,x]}\n        ref bg {ref['bg'][y,x]} disk {ref['disk'][y,x]}")
     for name, mask in (("d>1", d>1), ("d>2", d>2), ("cls", clsd), ("steps", steps_diff)):
         if mask.any():
             e = eps[mask]; print(f"   {name}: eps range [{e.min():.4f}, {e.max():.4f}]  ncross min {nc[mask].min()}  |eps|max {np.abs(e).max():.4f}")
-    for thr in (0.02, 0.03, 0.05, 0.08):
+    for thr in (0.005, 0.01, 0.015, 0.02):
         band = np.abs(eps) < thr
         print(f"   band |eps|<{thr}: {band.mean()*100:.2f}% of pixels, covers d>1: {(d>1)[band].sum()}/{(d>1).sum()}  d>2: {(d>2)[band].sum()}/{(d>2).sum()}, nc>=3 inside: {(nc>=3)[band].sum()}/{(nc>=3).sum()}")
 run("sd", [6,0,0.5], 90)

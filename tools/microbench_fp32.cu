@@ -45,6 +45,37 @@ template <int MODE> __global__ void __launch_bounds__(256) k(float* out, int ite
             } else if (MODE == 6) { // MUFU only
 #pragma unroll
                 for (int j = 0; j < 4; ++j) q[j] = rsq(q[j]);
+            } else if (MODE == 8) { // 6 FFMA + 1 FFMA2 interleaved
+#pragma unroll
+                for (int j = 0; j < 6; ++j) x[j] = fmaf(x[j], m, c);
+                v[u & 7] = fma2(v[u & 7], m2, c2);
+            } else if (MODE == 9) { // 4 FFMA + 2 FFMA2 interleaved (F F P F F P)
+                x[0] = fmaf(x[0], m, c); x[1] = fmaf(x[1], m, c); v[u & 3] = fma2(v[u & 3], m2, c2);
+                x[2] = fmaf(x[2], m, c); x[3] = fmaf(x[3], m, c); v[4 + (u & 3)] = fma2(v[4 + (u & 3)], m2, c2);
+            } else if (MODE == 10) { // 4 FFMA + 4 FFMA2 alternating
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { x[j] = fmaf(x[j], m, c); v[j] = fma2(v[j], m2, c2); }
+            } else if (MODE == 11) { // 5 FFMA + 1 FFMA2 + 1 FMNMX (odd scalar count between packed ops)
+#pragma unroll
+                for (int j = 0; j < 5; ++j) x[j] = fmaf(x[j], m, c);
+                v[u & 7] = fma2(v[u & 7], m2, c2);
+                mm[u & 3] = fminf(mm[u & 3], x[u & 3]);
+            } else if (MODE == 12) { // integrator-like: 10 FFMA + 2 FFMA2 + 1 MUFU + 2 FMNMX
+#pragma unroll
+                for (int j = 0; j < 5; ++j) x[j] = fmaf(x[j], m, c);
+                v[u & 7] = fma2(v[u & 7], m2, c2);
+#pragma unroll
+                for (int j = 0; j < 5; ++j) x[j] = fmaf(x[j], m, c);
+                v[(u + 1) & 7] = fma2(v[(u + 1) & 7], m2, c2);
+                q[u & 3] = rsq(q[u & 3]);
+                mm[u & 3] = fminf(mm[u & 3], x[u & 3]); mm[(u + 1) & 3] = fmaxf(mm[(u + 1) & 3], x[(u + 3) & 3]);
+            } else if (MODE == 13) { // all packed with the same non-FMA load per 2 rays: 6 FFMA2 + 1 MUFU + 2 FMNMX... x2 rays
+#pragma unroll
+                for (int j = 0; j < 7; ++j) v[j] = fma2(v[j], m2, c2);
+                q[u & 3] = rsq(q[u & 3]); q[(u + 1) & 3] = rsq(q[(u + 1) & 3]);
+                float a, b; up(v[u & 7], a, b);
+                mm[u & 3] = fminf(mm[u & 3], a); mm[(u + 1) & 3] = fmaxf(mm[(u + 1) & 3], b);
+                mm[(u + 2) & 3] = fminf(mm[(u + 2) & 3], b); mm[(u + 3) & 3] = fmaxf(mm[(u + 3) & 3], a);
             } else if (MODE == 7) { // 8 FFMA + 4 MUFU
 #pragma unroll
                 for (int j = 0; j < CHAINS; ++j) x[j] = fmaf(x[j], m, c);
@@ -89,6 +120,12 @@ int main() {
         run<4>("FFMA x8 + MUFU x1", 8, 1, occ);
         run<5>("FFMA2 x8 + MUFU x1", 16, 1, occ);
         run<7>("FFMA x8 + MUFU x4", 8, 4, occ);
+        run<8>("FFMA x6 + FFMA2 x1", 8, 0, occ);
+        run<9>("FFMA x4 + FFMA2 x2", 8, 0, occ);
+        run<10>("FFMA x4 + FFMA2 x4", 12, 0, occ);
+        run<11>("FFMA x5 + FFMA2 x1 + FMNMX", 7, 1, occ);
+        run<12>("FFMA x10+FFMA2 x2+MUFU+2FMNMX", 14, 3, occ);
+        run<13>("FFMA2 x7 + 2 MUFU + 4 FMNMX", 14, 6, occ);
         run<6>("MUFU x4", 0, 4, occ);
     }
     return 0;
