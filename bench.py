@@ -91,6 +91,43 @@ def cpu_port_frame(width, height, sky, tex, threads=None):
     return time.perf_counter() - t0, r["total_steps"], O.lib().orc_num_threads()
 
 
+def orbit_video_block(r, n_r, n_phi, rank, world, dist, torch, block=60, n_frames_total=3600):
+    """Frames/s of the orbit video path (render.py --video --orbit --n_frames 3600 -r fhd): frames
+    are dealt to ranks in 60-frame blocks (the statistics cadence); every rank replays the host
+    lifecycle ticks of all frames, and for its own block runs background + entity layer +
+    [statistics on the block's first frame] + compose + mips + ray march + bloom + composite and
+    reads the 8-bit frame back into pinned host memory.  PNG / x264 encoding is excluded."""
+    from black_hole_renderer_b200.driver import frame_owner, orbit_camera
+    from black_hole_renderer_b200.lifecycle import advance_lifecycle_frame, init_lifecycle_system
+    factories = init_lifecycle_system(r, n_r, n_phi, seed=42)
+    out = r.pinned_frame(np.uint8)
+    dt = 0.1
+    r.render_u8(POV, FOV, out=out)
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for frame in range(block * world):
+        t = frame * dt
+        if frame_owner(frame, world, block) != rank:
+            for f in factories.values():
+                f.tick(now=t, dt=dt)
+            continue
+        advance_lifecycle_frame(r, factories, t, dt, recompute_stats=(frame % block == 0))
+        r.render_u8(orbit_camera(POV, frame, n_frames_total, 360.0), FOV, out=out)
+    torch.cuda.synchronize()
+    sec = time.perf_counter() - t0
+    tt = torch.tensor([sec], dtype=torch.float64, device="cuda")
+    if dist:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    sec = float(tt.item())
+    return {"frames_per_s": block * world / sec, "frames": block * world, "seconds_max_over_ranks": sec,
+            "ms_per_frame_per_gpu": 1e3 * sec / block,
+            "includes": "host lifecycle ticks of all frames on every rank, background + entity + compose + mips "
+                        "kernels, statistics on each block's first frame, render, 8-bit frame D2H to pinned memory",
+            "excludes": "PNG / x264 encoding (host I/O)", "sharding": f"{block}-frame blocks round-robin, no collective"}
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU path (oracle port, all host threads)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -224,6 +261,9 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t.item())
 
+    # ---- orbit video (BASELINE.json configs[4]): one 60-frame block per rank, whole per-frame path ----
+    orbit = orbit_video_block(r, n_r, n_phi, rank, world, dist if world > 1 else None, torch)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -257,6 +297,7 @@ def main():
                      "peak_source": "scalar FFMA microbenchmark measured in this run (bhr_measure_fp32_peak); "
                                     "MEASURED_PEAKS.json holds no FP32 figure"},
         "clocks": clocks,
+        "orbit_video": orbit,
     }
     if not args.no_cpu_baseline and world == 1:      # CPU baseline: rank 0 at N = 1 only
         sys.path.insert(0, os.path.join(ROOT, "tests"))
