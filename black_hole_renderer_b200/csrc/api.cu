@@ -58,7 +58,6 @@ extern "C" int bhr_create(const bhr_config* cfg, bhr_ctx** out) {
     CREATE_CHECK(cudaMalloc(&ctx->final_u8, plane * 3));
     CREATE_CHECK(cudaMalloc(&ctx->cls, plane));
     CREATE_CHECK(cudaMalloc(&ctx->steps, plane * sizeof(int)));
-    CREATE_CHECK(cudaMalloc(&ctx->d_total_steps, sizeof(unsigned long long)));
     CREATE_CHECK(cudaMalloc(&ctx->d_flare_sums, 3 * sizeof(double)));
     // [0, plane) u64 re-trace entries of the safety net; then plane i32 band pixels
     CREATE_CHECK(cudaMalloc(&ctx->retrace_queue, plane * (sizeof(unsigned long long) + sizeof(int))));
@@ -66,8 +65,10 @@ extern "C" int bhr_create(const bhr_config* cfg, bhr_ctx** out) {
     CREATE_CHECK(cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, cfg->device));
     ctx->persistent = 1;
     ctx->pblock_big = 1;
-    CREATE_CHECK(cudaMalloc(&ctx->d_queue_count, 4 * sizeof(unsigned int)));
-    CREATE_CHECK(cudaMemset(ctx->d_queue_count, 0, 4 * sizeof(unsigned int)));
+    // [0] re-trace queue tail, [1] band count, [2] band head, [3] tile counter, [4..5] u64 step total
+    CREATE_CHECK(cudaMalloc(&ctx->d_queue_count, 8 * sizeof(unsigned int)));
+    CREATE_CHECK(cudaMemset(ctx->d_queue_count, 0, 8 * sizeof(unsigned int)));
+    ctx->d_total_steps = (unsigned long long*)(ctx->d_queue_count + 4);
     ctx->retrace_min_cross = 3;
     ctx->retrace_band = 0.02f;
     CREATE_CHECK(cudaMemset(ctx->bg, 0, plane * 3 * sizeof(float)));
@@ -76,7 +77,6 @@ extern "C" int bhr_create(const bhr_config* cfg, bhr_ctx** out) {
     CREATE_CHECK(cudaMemset(ctx->blur, 0, plane * 3 * sizeof(float)));
     CREATE_CHECK(cudaMemset(ctx->cls, 0, plane));
     CREATE_CHECK(cudaMemset(ctx->steps, 0, plane * sizeof(int)));
-    CREATE_CHECK(cudaMemset(ctx->d_total_steps, 0, sizeof(unsigned long long)));
     for (int k = 0; k < 6; ++k) CREATE_CHECK(cudaEventCreate(&ctx->ev[k]));
     tint_6000(ctx->tint);
     ctx->stats[0] = 0.5f; ctx->stats[1] = 0.5f;    // render.py:3533
@@ -94,7 +94,7 @@ extern "C" void bhr_destroy(bhr_ctx* ctx) {
     cudaSetDevice(ctx->cfg.device);
     if (ctx->own_stream) { cudaStreamSynchronize(ctx->own_stream); }
     void* ptrs[] = {ctx->sky, ctx->mips, ctx->tex_staging, ctx->bg, ctx->disk, ctx->hblur, ctx->blur, ctx->final_f32,
-                    ctx->final_u8, ctx->cls, ctx->steps, ctx->d_total_steps, ctx->d_flare_sums, ctx->retrace_queue, ctx->d_queue_count, ctx->d_wtab, ctx->d_wsum_x,
+                    ctx->final_u8, ctx->cls, ctx->steps, ctx->d_flare_sums, ctx->retrace_queue, ctx->d_queue_count, ctx->d_wtab, ctx->d_wsum_x,
                     ctx->d_wsum_y, ctx->comp, ctx->edge, ctx->omega_rows, ctx->row_stats, ctx->d_entities};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int k = 0; k < 6; ++k) if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
