@@ -71,7 +71,7 @@ struct bhr_ctx {
     int bloom_R; float sigma_scale;
     float* d_wtab;                     // 3 x wtab_stride (2R+1 weights + zero padding)
     int wtab_stride;
-    float* d_wsum_x;                   // 3 x W   in-bounds weight sums (sequential f32 order)
+    float* d_wsum_x;                   // 3 x W   1 / in-bounds weight sums (summed in sequential f32 order)
     float* d_wsum_y;                   // 3 x H
 
     // disk-texture pipeline

@@ -49,9 +49,13 @@ __global__ void __launch_bounds__(256) bloom_h_kernel(const float* __restrict__ 
     const bool row_ok = y < row1;
     if (row_ok) {
         const float* srow = src + ch * plane + (size_t)y * W;
+        // s = lane + 32 i  ->  (s % 10, s / 10) kept incrementally: 32 = 3 * 10 + 2
+        int sr = lane % P_OUT, sq = lane / P_OUT;
         for (int s = lane; s < seg; s += 32) {
             const int x = x0 - R + s;
-            row[(s % P_OUT) * pitch + s / P_OUT] = (x >= 0 && x < W) ? __ldg(srow + x) : 0.0f;
+            row[sr * pitch + sq] = (x >= 0 && x < W) ? __ldg(srow + x) : 0.0f;
+            sr += 32 % P_OUT; sq += 32 / P_OUT;
+            if (sr >= P_OUT) { sr -= P_OUT; ++sq; }
         }
     }
     __syncthreads();
@@ -80,13 +84,13 @@ __global__ void __launch_bounds__(256) bloom_h_kernel(const float* __restrict__ 
     __syncwarp();
     float* drow = dst + ch * plane + (size_t)y * W;
     const float* ws = wsum_x + ch * W;
-    for (int i = lane; i < 32 * P_OUT; i += 32) {
-        const int x = x0 + i;
-        if (x < W) {
-            const float wsum = ws[x];
-            const float a = row[(i % P_OUT) * pitch + i / P_OUT];
-            drow[x] = wsum > 0.0f ? a / wsum : 0.0f;
-        }
+    int ir = lane % P_OUT, iq = lane / P_OUT;
+#pragma unroll
+    for (int j = 0; j < P_OUT; ++j) {
+        const int x = x0 + lane + 32 * j;
+        if (x < W) drow[x] = row[ir * pitch + iq] * ws[x];       // ws = 1 / in-bounds weight sum (0 if none)
+        ir += 32 % P_OUT; iq += 32 / P_OUT;
+        if (ir >= P_OUT) { ir -= P_OUT; ++iq; }
     }
 }
 
@@ -228,8 +232,7 @@ __global__ void __launch_bounds__(256) bloom_v_kernel(const float* __restrict__ 
     for (int p = 0; p < P_OUT; ++p) {
         const int y = y0 + p;
         if (y < row1) {
-            const float wsum = wsum_y[ch * H + y];
-            dst[(size_t)y * W + x] = wsum > 0.0f ? acc[p] / wsum : 0.0f;
+            dst[(size_t)y * W + x] = acc[p] * wsum_y[ch * H + y];   // 1 / in-bounds weight sum (0 if none)
         }
     }
 }
@@ -336,7 +339,8 @@ __global__ void __launch_bounds__(256) flare_sums_kernel(const float* __restrict
 }  // namespace
 
 // weights exp(-d^2 / (sigma2 * sigma_scale)) (render.py:3058-3060) evaluated like the oracle
-// (double exp rounded once), plus in-bounds weight sums in the reference's tap order
+// (double exp rounded once), plus the reciprocals of the in-bounds weight sums (summed in the
+// reference's tap order; the kernels multiply by the reciprocal instead of dividing: <= 1 ulp)
 int bhr_setup_bloom_tables(bhr_ctx* ctx) {
     const int W = ctx->W, H = ctx->H;
     const int R = (int)(W * 0.02);                          // render.py:3914
@@ -358,12 +362,12 @@ int bhr_setup_bloom_tables(bhr_ctx* ctx) {
         for (int x = 0; x < W; ++x) {
             float s = 0.0f;
             for (int d = -R; d <= R; ++d) if (x + d >= 0 && x + d < W) s += wt[c * stride + d + R];
-            wx[c * W + x] = s;
+            wx[c * W + x] = s > 0.0f ? 1.0f / s : 0.0f;
         }
         for (int y = 0; y < H; ++y) {
             float s = 0.0f;
             for (int d = -R; d <= R; ++d) if (y + d >= 0 && y + d < H) s += wt[c * stride + d + R];
-            wy[c * H + y] = s;
+            wy[c * H + y] = s > 0.0f ? 1.0f / s : 0.0f;
         }
     }
     BHR_CUDA(ctx, cudaMalloc(&ctx->d_wtab, (size_t)3 * stride * sizeof(float)));
