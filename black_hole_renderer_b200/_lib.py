@@ -70,6 +70,9 @@ SIGNATURES = {
     "bhr_upload_comp": (C.c_int, [_P, _FP]),
     "bhr_compose_texture": (C.c_int, [_P, C.c_float, C.c_int, C.c_float]),
     "bhr_eval_noise": (C.c_int, [_P, _FP, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, _FP]),
+    "bhr_stats_prepare": (C.c_int, [_P, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "bhr_stats_select": (C.c_int, [_P, C.c_uint64, C.c_uint64, _FP]),
+    "bhr_stats_rows": (C.c_int, [_P, C.c_float, C.c_int, C.c_int, _FP]),
     "bhr_measure_fp32_peak": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "bhr_selftest_div6": (C.c_int, [C.c_int, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]),
 }

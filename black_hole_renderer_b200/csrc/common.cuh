@@ -80,6 +80,8 @@ struct bhr_ctx {
     float stats[2];
     int bg_ready, az_freq; float az_shear;
     bhr_entity* d_entities; int entities_cap;
+    float* stats_scratch;              // device statistics: density / structure planes, row results (stats.cu)
+    void* stats_state;
 
     cudaEvent_t ev[6];
     int ev_valid;

@@ -38,6 +38,35 @@ class _Field:
         return self._getter()
 
 
+def numpy_quantile_neighbours(n, q):
+    """(lo, hi, gamma) of numpy's method="linear" quantile of an n-element float32 array: the two
+    sorted positions it reads and the weight it interpolates with.  `q` is the quantile as numpy
+    has it at that point: a float32 scalar (np.percentile divides by float32(100), np.quantile
+    casts a Python float to the array's dtype), so the virtual index -- and with it the weight --
+    is a FLOAT32 quantity (numpy/lib/_function_base_impl.py: _QuantileMethods['linear'],
+    _get_indexes, _get_gamma).  tests/test_host.py holds this to np.percentile / np.quantile bit for bit."""
+    q = np.asanyarray(q)
+    vi = np.asanyarray((n - 1) * q)         # _QuantileMethods['linear']['get_virtual_index']
+    prev = np.floor(vi)
+    nxt = prev + 1
+    if vi >= n - 1:
+        prev, nxt = np.float32(n - 1), np.float32(n - 1)
+    if vi < 0:
+        prev, nxt = np.float32(0), np.float32(0)
+    lo, hi = int(prev), int(nxt)
+    gamma = np.asanyarray(vi - np.intp(lo) if vi < n - 1 else vi - np.intp(-1), dtype=vi.dtype)
+    return lo, hi, gamma
+
+
+def numpy_linear_lerp(a, b, t):
+    """numpy's _lerp on the two neighbours (float32 arithmetic for float32 inputs)."""
+    a, b = np.asanyarray(a), np.asanyarray(b)
+    diff = np.subtract(b, a)
+    out = np.asanyarray(np.add(a, diff * t))
+    np.subtract(b, diff * (1 - t), out=out, where=t >= 0.5, casting="unsafe", dtype=type(out.dtype))
+    return out[()] if out.ndim == 0 else out
+
+
 def compute_edge_alpha(height, inner_soft=0.1, outer_soft=0.3):
     """Soft radial edges of the disk alpha (reference: compute_edge_alpha, render.py:437-445):
     cubic ramp over the inner 10 % of rows, quadratic fall-off over the outer 30 %."""
@@ -308,23 +337,33 @@ class Renderer:
     def recompute_interactive_stats(self):
         """Normalisation statistics from the current component field (render.py:3655-3712):
         98th percentile of the density mix, 95th percentile of the positive structure
-        temperature, per-row max / 70 % quantile of the scaled structure temperature."""
-        comp = self._comp_field.to_numpy()
-        edge = self._bg_edge_np
-        rt_w = 0.20 if self._param_enable_rt else 0.0
-        dm = comp[12]
-        density = (0.15 + 0.10 * comp[1] + 0.30 * comp[3] + 0.20 * comp[9] + 0.30 * comp[5]
-                   + rt_w * comp[7]) * dm
-        density *= edge[:, None]
-        p98 = max(float(np.percentile(density, 98)), 0.01)
-        struct = (comp[2] + comp[4] + comp[6] + comp[8] + comp[10]) * dm
-        positive = struct > 0
-        scale = float(np.percentile(struct[positive], 95)) if np.any(positive) else 1.0
+        temperature, per-row max / 70 % quantile of the scaled structure temperature.
+
+        The reference reads the whole field back and calls np.percentile / np.quantile; here the
+        device returns the exact order statistics on both sides of each quantile's virtual index
+        (radix select / per-row sort, csrc/stats.cu) and `numpy_linear_lerp` applies numpy's own
+        float32 interpolation to them -- the same numbers without the 63 MB read-back."""
+        n_tot, n_pos = C.c_uint64(), C.c_uint64()
+        self._check(self._lib.bhr_stats_prepare(self._ctx, int(self._param_enable_rt),
+                                                C.byref(n_tot), C.byref(n_pos)))
+        n_tot, n_pos = int(n_tot.value), int(n_pos.value)
+        lo_d, hi_d, g_d = numpy_quantile_neighbours(n_tot, np.true_divide(98, np.float32(100)))
+        lo_s, hi_s, g_s = numpy_quantile_neighbours(max(n_pos, 1), np.true_divide(95, np.float32(100)))
+        vals = np.zeros(4, dtype=np.float32)
+        self._check(self._lib.bhr_stats_select(self._ctx, lo_d, lo_s, _fp(vals)))
+        d_hi = vals[1] if hi_d != lo_d else vals[0]
+        s_hi = vals[3] if hi_s != lo_s else vals[2]
+        p98 = max(float(numpy_linear_lerp(vals[0], d_hi, g_d)), 0.01)
+        scale = float(numpy_linear_lerp(vals[2], s_hi, g_s)) if n_pos > 0 else 1.0
         scale = max(scale, 0.01)
-        scaled = np.clip(struct / (scale + 1e-6) * 0.8, 0, 1.2)
-        row_max = np.max(scaled, axis=1).astype(np.float32)
-        row_p70 = np.quantile(scaled, 0.7, axis=1).astype(np.float32)
-        tb_max = np.max(comp[0], axis=1).astype(np.float32)
+        # struct / (scale + 1e-6) * 0.8: the Python-float divisor becomes a float32 operand
+        denom = np.float32(scale + 1e-6)
+        lo_r, hi_r, g_r = numpy_quantile_neighbours(self.dtex_w, np.asanyarray(0.7, dtype=np.float32))
+        rows = np.zeros((self.dtex_h, 4), dtype=np.float32)
+        self._check(self._lib.bhr_stats_rows(self._ctx, float(denom), lo_r, hi_r, _fp(rows)))
+        row_max = rows[:, 0]
+        row_p70 = numpy_linear_lerp(rows[:, 1], rows[:, 2], g_r).astype(np.float32)
+        tb_max = rows[:, 3]
         row_max = np.maximum(row_max, tb_max)
         row_p70 = np.maximum(row_p70, tb_max * 0.8)
         self._stats = np.array([p98, scale], dtype=np.float32)

@@ -152,8 +152,20 @@ typedef struct {
     double p[8];                  /* kind-specific parameters, see texture.cu  */
 } bhr_entity;
 int bhr_accumulate_entities(bhr_ctx* ctx, const bhr_entity* entities, int n);
-/* recompute_interactive_stats (render.py:3655-3712) stays on the host at first: read comp back,
- * then upload the two scalars + per-row (max, p70). */
+/* recompute_interactive_stats (render.py:3655-3712) on the device.  The reference runs
+ * np.percentile / np.quantile on the host; here the device returns the exact order statistics next
+ * to each quantile's virtual index and the caller applies numpy's interpolation to them:
+ *   bhr_stats_prepare: density / structure planes (numpy's f32 operation order); returns the texel
+ *                      count and the number of texels with structure > 0;
+ *   bhr_stats_select:  out = {density[rank_d], density[rank_d + 1], struct+[rank_s], struct+[rank_s + 1]}
+ *                      in sorted order (struct+ = the positive structure values; the upper neighbour
+ *                      is clipped to the last element);
+ *   bhr_stats_rows:    out (n_r, 4) = per row {max, sorted[lo], sorted[hi]} of
+ *                      clip(structure / denom * 0.8, 0, 1.2) and the row max of the base temperature.
+ * The results are pushed back with bhr_set_stats. */
+int bhr_stats_prepare(bhr_ctx* ctx, int enable_rt, uint64_t* n_total, uint64_t* n_positive);
+int bhr_stats_select(bhr_ctx* ctx, uint64_t rank_density, uint64_t rank_struct, float out[4]);
+int bhr_stats_rows(bhr_ctx* ctx, float denom, int lo, int hi, float* out /* (n_r, 4) */);
 int bhr_set_stats(bhr_ctx* ctx, float density_p98, float struct_scale, const float* row_stats /* (n_r, 2) */);
 int bhr_upload_comp(bhr_ctx* ctx, const float* comp /* (13, n_r, n_phi) */);
 /* compose_interactive_texture (render.py:3714-3767): compose kernel + mip kernels */

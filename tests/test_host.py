@@ -115,3 +115,24 @@ def test_cli_surface():
                 ["--disk_texture", "x.png", "--video"]):
         with pytest.raises(ValueError):
             render.validate_args(render.parse_args(bad))
+
+
+def test_numpy_quantile_helpers_match_numpy_bit_for_bit():
+    """The device statistics return order statistics; the host applies numpy's interpolation to
+    them with these helpers, which must reproduce np.percentile / np.quantile exactly (float32
+    virtual index and all)."""
+    from black_hole_renderer_b200.renderer import numpy_linear_lerp, numpy_quantile_neighbours
+    rng = np.random.default_rng(1)
+    for n in [1, 2, 3, 7, 100, 2912, 5824, 416 * 2912]:
+        a = rng.random(n).astype(np.float32) ** 3
+        srt = np.sort(a)
+        for q in [98, 95, 50, 0, 100]:
+            lo, hi, g = numpy_quantile_neighbours(n, np.true_divide(q, np.float32(100)))
+            got, want = numpy_linear_lerp(srt[lo], srt[hi], g), np.percentile(a, q)
+            assert got == want and got.dtype == want.dtype, (n, q)
+        lo, hi, g = numpy_quantile_neighbours(n, np.asanyarray(0.7, dtype=np.float32))
+        assert numpy_linear_lerp(srt[lo], srt[hi], g) == np.quantile(a, 0.7)
+    rows = rng.random((50, 2912)).astype(np.float32)
+    lo, hi, g = numpy_quantile_neighbours(2912, np.asanyarray(0.7, dtype=np.float32))
+    srt = np.sort(rows, axis=1)
+    assert np.array_equal(numpy_linear_lerp(srt[:, lo], srt[:, hi], g), np.quantile(rows, 0.7, axis=1))
