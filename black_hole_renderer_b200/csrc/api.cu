@@ -95,9 +95,11 @@ extern "C" void bhr_destroy(bhr_ctx* ctx) {
     if (ctx->own_stream) { cudaStreamSynchronize(ctx->own_stream); }
     void* ptrs[] = {ctx->sky, ctx->mips, ctx->tex_staging, ctx->bg, ctx->disk, ctx->hblur, ctx->blur, ctx->final_f32,
                     ctx->final_u8, ctx->cls, ctx->steps, ctx->d_flare_sums, ctx->retrace_queue, ctx->d_queue_count, ctx->d_wtab, ctx->d_wsum_x,
-                    ctx->d_wsum_y, ctx->comp, ctx->edge, ctx->omega_rows, ctx->row_stats, ctx->d_entities, ctx->stats_scratch, ctx->stats_state};
+                    ctx->d_wsum_y, ctx->comp, ctx->edge, ctx->omega_rows, ctx->row_stats, ctx->d_entities, ctx->stats_scratch, ctx->stats_state, ctx->d_coltab};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int k = 0; k < 6; ++k) if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
+    for (int k = 0; k < 4; ++k) if (ctx->ent_ev[k]) cudaEventDestroy(ctx->ent_ev[k]);
+    if (ctx->h_entities) cudaFreeHost(ctx->h_entities);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     free(ctx);
 }

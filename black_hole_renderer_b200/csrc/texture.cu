@@ -207,68 +207,128 @@ __device__ __forceinline__ float py_modf32(float a, float b) {
     return m;
 }
 
+// Hotspot / rt_spike azimuthal profiles exp(kappa (cos(phi - phi0) - 1)) depend on the (rolled)
+// source column only: one table row of n_phi doubles per such entity.
+__global__ void __launch_bounds__(256) entity_coltab_kernel(const bhr_entity* __restrict__ ents, const int* __restrict__ slot_ent,
+                                                            int n_phi, double* __restrict__ coltab) {
+    const int src = blockIdx.x * 256 + threadIdx.x;
+    if (src >= n_phi) return;
+    const bhr_entity& E = ents[slot_ent[blockIdx.y]];
+    const double phi = (double)src * (6.283185307179586 / (double)n_phi);
+    const double kappa = 1.5 / (E.p[2] * E.p[2]);
+    coltab[(size_t)blockIdx.y * n_phi + src] = exp(kappa * (cos(phi - E.p[0]) - 1.0));
+}
+
+// one entity that touches the block's row, with everything that depends on (entity, row) only
+struct RowEntity {
+    double a, b, c;          // filament: scale_d * r_w, scale_t * r_w, 1 / (2 sigma_phi^2); others: r_prof, intensity, -
+    const double* col;       // hotspot / rt_spike: azimuthal profile table
+    float ctr;               // filament: blob centre (float32, render.py:3633); others: fade alpha
+    float tfac;              // rt_spike: delta_T
+    int kind, shift;
+};
+
+constexpr int kEntCols = 1024;     // columns per block (4 per thread)
+
 __global__ void __launch_bounds__(256) entity_accumulate_kernel(float* __restrict__ comp, int n_r, int n_phi,
                                                                 const bhr_entity* __restrict__ ents, int n_ent,
-                                                                const float* __restrict__ omega_rows) {
+                                                                const float* __restrict__ omega_rows,
+                                                                const int* __restrict__ ent_slot,
+                                                                const double* __restrict__ coltab) {
+    extern __shared__ __align__(16) unsigned char ent_smem[];
+    RowEntity* list = reinterpret_cast<RowEntity*>(ent_smem);
+    __shared__ int warp_count[8];
+    __shared__ int n_list;
+    const int ri = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t plane = (size_t)n_r * n_phi;
-    const size_t o = blockIdx.x * (size_t)256 + threadIdx.x;
-    if (o >= plane) return;
-    const int ri = (int)(o / n_phi), pi = (int)(o % n_phi);
-    const double TWO_PI = 6.283185307179586;
+    const double TWO_PI = 6.283185307179586, PI = 3.141592653589793;
     const double r_norm = (ri == n_r - 1) ? 1.0 : (double)ri * (1.0 / (double)(n_r - 1));   // np.linspace(0, 1, n_r)
     const double phi_step = TWO_PI / (double)n_phi;                                           // linspace(endpoint=False)
     const float om = omega_rows[ri];
-    float acc[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
-    for (int e = 0; e < n_ent; ++e) {
-        const bhr_entity& E = ents[e];
-        if (ri < E.row_begin || ri >= E.row_end) continue;
-        if (E.kind == 0) {
-            double dr = r_norm - E.p[1];
-            double r_w = exp(-(dr * dr) * E.p[2]);
-            // center = (source_phi - omega[ri] * age) % 2pi evaluates in float32 in the reference
-            // (np.float32 scalar with weak Python floats), render.py:3633
-            float center = py_modf32(__fsub_rn((float)E.p[0], __fmul_rn(om, (float)E.age)), 6.2831855f);
-            double d_phi = (double)pi * phi_step - (double)center;
-            d_phi = d_phi - TWO_PI * rint(d_phi / TWO_PI);
-            double prof = exp(-d_phi * d_phi * E.p[3]);
-            acc[0] = (float)((double)acc[0] + prof * (E.p[4] * r_w));
-            acc[1] = (float)((double)acc[1] + prof * (E.p[5] * r_w));
-        } else {
-            // shift = int(age * omega[ri] / (2 pi) * n_phi) in float32, render.py:3645
-            float sf = __fmul_rn(__fdiv_rn(__fmul_rn((float)E.age, om), 6.2831855f), (float)n_phi);
-            int shift = (int)sf;
-            int src = (pi + shift) % n_phi;
-            if (src < 0) src += n_phi;
-            double phi = (double)src * phi_step;
-            double kappa = 1.5 / (E.p[2] * E.p[2]);
-            double phi_prof = exp(kappa * (cos(phi - E.p[0]) - 1.0));
-            const float alpha = (float)E.scale;
-            if (E.kind == 1) {
-                double rd = r_norm - E.p[1];
-                double q = rd / (E.p[3] + 1e-8);
-                double r_prof = exp(-0.5 * (q * q));
-                float dens = (float)(phi_prof * r_prof * E.p[4]);
-                float temp = __fmul_rn(dens, 0.12f);
-                dens = fminf(fmaxf(dens, 0.0f), 1.0f);
-                temp = fminf(fmaxf(temp, 0.0f), 1.0f);
-                acc[4] = __fadd_rn(acc[4], __fmul_rn(dens, alpha));
-                acc[5] = __fadd_rn(acc[5], __fmul_rn(temp, alpha));
+    if (threadIdx.x == 0) n_list = 0;
+    __syncthreads();
+    // ---- the entities of this row, in list order (ordered compaction, 256 candidates at a time) ----
+    for (int e0 = 0; e0 < n_ent; e0 += 256) {
+        const int e = e0 + threadIdx.x;
+        const bool hit = e < n_ent && ri >= ents[e].row_begin && ri < ents[e].row_end;
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (lane == 0) warp_count[warp] = __popc(m);
+        __syncthreads();
+        int base = n_list;
+        for (int w = 0; w < warp; ++w) base += warp_count[w];
+        if (hit) {
+            const bhr_entity& E = ents[e];
+            RowEntity R;
+            R.kind = E.kind; R.col = nullptr; R.shift = 0; R.tfac = 0.0f; R.c = 0.0;
+            const double rd = r_norm - E.p[1];
+            if (E.kind == 0) {
+                const double r_w = exp(-(rd * rd) * E.p[2]);
+                R.a = E.p[4] * r_w; R.b = E.p[5] * r_w; R.c = E.p[3];
+                // center = (source_phi - omega[ri] * age) % 2pi evaluates in float32 in the reference
+                // (np.float32 scalar with weak Python floats), render.py:3633
+                R.ctr = py_modf32(__fsub_rn((float)E.p[0], __fmul_rn(om, (float)E.age)), 6.2831855f);
             } else {
-                double rd = r_norm - E.p[1];
-                double fo = fmin(fmax(E.p[3] * 2 - rd, 0.0), 1.0);
-                double fi = fmin(fmax(rd / (E.p[3] * 0.3 + 1e-8), 0.0), 1.0);
-                double q = rd / (E.p[3] * 0.4 + 1e-8);
-                double r_prof = exp(-0.5 * (q * q)) * fo * fi;
-                float dens = (float)(phi_prof * r_prof * E.p[4]);
-                float temp = __fmul_rn(dens, (float)E.p[5]);
-                dens = fminf(fmaxf(dens, 0.0f), 1.0f);
-                acc[2] = __fadd_rn(acc[2], __fmul_rn(dens, alpha));
-                acc[3] = __fadd_rn(acc[3], __fmul_rn(temp, alpha));
+                // shift = int(age * omega[ri] / (2 pi) * n_phi) in float32, render.py:3645
+                R.shift = (int)__fmul_rn(__fdiv_rn(__fmul_rn((float)E.age, om), 6.2831855f), (float)n_phi);
+                R.col = coltab + (size_t)ent_slot[e] * n_phi;
+                R.ctr = (float)E.scale;
+                R.b = E.p[4];
+                if (E.kind == 1) {
+                    const double q = rd / (E.p[3] + 1e-8);
+                    R.a = exp(-0.5 * (q * q));
+                } else {
+                    const double fo = fmin(fmax(E.p[3] * 2 - rd, 0.0), 1.0);
+                    const double fi = fmin(fmax(rd / (E.p[3] * 0.3 + 1e-8), 0.0), 1.0);
+                    const double q = rd / (E.p[3] * 0.4 + 1e-8);
+                    R.a = exp(-0.5 * (q * q)) * fo * fi;
+                    R.tfac = (float)E.p[5];
+                }
+            }
+            list[base + __popc(m & ((1u << lane) - 1u))] = R;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) { int t = n_list; for (int w = 0; w < 8; ++w) t += warp_count[w]; n_list = t; }
+        __syncthreads();
+    }
+    const int n = n_list;
+    // ---- accumulate: f32 sums in list order, float64 profiles (numpy's order and precision) ----
+    for (int pi = blockIdx.x * kEntCols + threadIdx.x; pi < min(n_phi, (int)(blockIdx.x + 1) * kEntCols); pi += 256) {
+        float acc[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+        const double phi_tex = (double)pi * phi_step;
+        for (int k = 0; k < n; ++k) {
+            const RowEntity& R = list[k];
+            if (R.kind == 0) {
+                double d_phi = phi_tex - (double)R.ctr;
+                // d_phi - 2 pi rint(d_phi / (2 pi)) for |d_phi| < 3 pi: the quotient rounds above 0.5
+                // exactly when d_phi > pi (pi = 2 pi / 2 in double), so two comparisons replace the division
+                if (d_phi > PI) d_phi -= TWO_PI; else if (d_phi < -PI) d_phi += TWO_PI;
+                const double prof = exp(-d_phi * d_phi * R.c);
+                acc[0] = (float)((double)acc[0] + prof * R.a);
+                acc[1] = (float)((double)acc[1] + prof * R.b);
+            } else {
+                int src = (pi + R.shift) % n_phi;
+                if (src < 0) src += n_phi;
+                const double phi_prof = R.col[src];
+                float dens = (float)(phi_prof * R.a * R.b);
+                if (R.kind == 1) {
+                    float temp = __fmul_rn(dens, 0.12f);
+                    dens = fminf(fmaxf(dens, 0.0f), 1.0f);
+                    temp = fminf(fmaxf(temp, 0.0f), 1.0f);
+                    acc[4] = __fadd_rn(acc[4], __fmul_rn(dens, R.ctr));
+                    acc[5] = __fadd_rn(acc[5], __fmul_rn(temp, R.ctr));
+                } else {
+                    const float temp = __fmul_rn(dens, R.tfac);
+                    dens = fminf(fmaxf(dens, 0.0f), 1.0f);
+                    acc[2] = __fadd_rn(acc[2], __fmul_rn(dens, R.ctr));
+                    acc[3] = __fadd_rn(acc[3], __fmul_rn(temp, R.ctr));
+                }
             }
         }
-    }
+        const size_t o = (size_t)ri * n_phi + pi;
 #pragma unroll
-    for (int k = 0; k < 6; ++k) comp[(5 + k) * plane + o] = acc[k];
+        for (int k = 0; k < 6; ++k) comp[(5 + k) * plane + o] = acc[k];
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -416,20 +476,60 @@ extern "C" int bhr_generate_background(bhr_ctx* ctx, float t) {
 extern "C" int bhr_accumulate_entities(bhr_ctx* ctx, const bhr_entity* entities, int n) {
     if (!ctx || (n > 0 && !entities)) return BHR_ERR_INVALID;
     if (!ctx->bg_ready) BHR_FAIL(ctx, BHR_ERR_STATE, "Must call init_background_layer() first");
+    // host staging ring (pinned): the caller's array may be reused as soon as we return, and the
+    // upload must not wait for the frames still in flight on the stream
+    const int n_slots_ring = 4;
     if (n > ctx->entities_cap) {
-        if (ctx->d_entities) cudaFree(ctx->d_entities);
-        ctx->entities_cap = n + 256;
-        BHR_CUDA(ctx, cudaMalloc(&ctx->d_entities, (size_t)ctx->entities_cap * sizeof(bhr_entity)));
-    }
-    if (n > 0) {
-        BHR_CUDA(ctx, cudaMemcpyAsync(ctx->d_entities, entities, (size_t)n * sizeof(bhr_entity), cudaMemcpyHostToDevice, ctx->stream));
-        // the host array may be reused by the caller as soon as we return
         BHR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->d_entities) cudaFree(ctx->d_entities);
+        if (ctx->h_entities) cudaFreeHost(ctx->h_entities);
+        if (ctx->d_coltab) cudaFree(ctx->d_coltab);
+        ctx->entities_cap = n + 256;
+        const size_t per = (size_t)ctx->entities_cap * (sizeof(bhr_entity) + 2 * sizeof(int));
+        BHR_CUDA(ctx, cudaMalloc(&ctx->d_entities, per * n_slots_ring));
+        BHR_CUDA(ctx, cudaMallocHost(&ctx->h_entities, per * n_slots_ring));
+        BHR_CUDA(ctx, cudaMalloc(&ctx->d_coltab, (size_t)ctx->entities_cap * ctx->n_phi * sizeof(double) * 2));
+        for (int k = 0; k < n_slots_ring; ++k)
+            if (!ctx->ent_ev[k]) BHR_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ent_ev[k], cudaEventDisableTiming));
+        ctx->ent_ring = 0;
     }
     const size_t plane = (size_t)ctx->n_r * ctx->n_phi;
-    entity_accumulate_kernel<<<(unsigned)((plane + 255) / 256), 256, 0, ctx->stream>>>(
-        ctx->comp, ctx->n_r, ctx->n_phi, ctx->d_entities, n, ctx->omega_rows);
+    if (n == 0) {
+        BHR_CUDA(ctx, cudaMemsetAsync(ctx->comp + 5 * plane, 0, 6 * plane * sizeof(float), ctx->stream));
+        return BHR_OK;
+    }
+    const int ring = ctx->ent_ring;
+    ctx->ent_ring = (ring + 1) % n_slots_ring;
+    const size_t per = (size_t)ctx->entities_cap * (sizeof(bhr_entity) + 2 * sizeof(int));
+    BHR_CUDA(ctx, cudaEventSynchronize(ctx->ent_ev[ring]));       // the kernels that last read this slot are done
+    char* h = (char*)ctx->h_entities + per * ring;
+    char* d = (char*)ctx->d_entities + per * ring;
+    bhr_entity* h_ent = (bhr_entity*)h;
+    int* h_slot = (int*)(h + (size_t)ctx->entities_cap * sizeof(bhr_entity));    // entity -> table row
+    int* h_slot_ent = h_slot + ctx->entities_cap;                                // table row -> entity
+    memcpy(h_ent, entities, (size_t)n * sizeof(bhr_entity));
+    int n_tab = 0;
+    for (int e = 0; e < n; ++e) {
+        if (entities[e].kind != 0) { h_slot[e] = n_tab; h_slot_ent[n_tab++] = e; } else h_slot[e] = -1;
+    }
+    BHR_CUDA(ctx, cudaMemcpyAsync(d, h, per, cudaMemcpyHostToDevice, ctx->stream));
+    const bhr_entity* d_ent = (const bhr_entity*)d;
+    const int* d_slot = (const int*)(d + (size_t)ctx->entities_cap * sizeof(bhr_entity));
+    const int* d_slot_ent = d_slot + ctx->entities_cap;
+    double* coltab = ctx->d_coltab + (size_t)(ring & 1) * ctx->entities_cap * ctx->n_phi;
+    if (n_tab > 0) {
+        dim3 g(bhr_div_up(ctx->n_phi, 256), n_tab);
+        entity_coltab_kernel<<<g, 256, 0, ctx->stream>>>(d_ent, d_slot_ent, ctx->n_phi, coltab);
+    }
+    const size_t smem = (size_t)n * sizeof(RowEntity);
+    if (smem > 200 * 1024) BHR_FAIL(ctx, BHR_ERR_INVALID, "too many entities (%d) for the per-row list", n);
+    if (smem > 48 * 1024)
+        BHR_CUDA(ctx, cudaFuncSetAttribute(entity_accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(bhr_div_up(ctx->n_phi, kEntCols), ctx->n_r);
+    entity_accumulate_kernel<<<grid, 256, smem, ctx->stream>>>(ctx->comp, ctx->n_r, ctx->n_phi, d_ent, n, ctx->omega_rows,
+                                                               d_slot, coltab);
     BHR_CUDA(ctx, cudaGetLastError());
+    BHR_CUDA(ctx, cudaEventRecord(ctx->ent_ev[ring], ctx->stream));
     return BHR_OK;
 }
 
