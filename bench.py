@@ -100,21 +100,29 @@ def orbit_video_block(r, n_r, n_phi, rank, world, dist, torch, block=60, n_frame
     from black_hole_renderer_b200.driver import frame_owner, orbit_camera
     from black_hole_renderer_b200.lifecycle import advance_lifecycle_frame, init_lifecycle_system
     factories = init_lifecycle_system(r, n_r, n_phi, seed=42)
-    out = r.pinned_frame(np.uint8)
+    bufs = [r.pinned_frame(np.uint8) for _ in range(2)]
     dt = 0.1
-    r.render_u8(POV, FOV, out=out)
+    r.render_u8(POV, FOV, out=bufs[0])
     torch.cuda.synchronize()
     if dist:
         dist.barrier()
     t0 = time.perf_counter()
+    issued, in_flight = 0, None
     for frame in range(block * world):
         t = frame * dt
         if frame_owner(frame, world, block) != rank:
             for f in factories.values():
                 f.tick(now=t, dt=dt)
             continue
+        # pipelined like driver.render_video: enqueue frame i, then wait for frame i - 1
         advance_lifecycle_frame(r, factories, t, dt, recompute_stats=(frame % block == 0))
-        r.render_u8(orbit_camera(POV, frame, n_frames_total, 360.0), FOV, out=out)
+        r.render_u8_async(orbit_camera(POV, frame, n_frames_total, 360.0), FOV, bufs[issued % 2], issued % 2)
+        if in_flight is not None:
+            r.wait_frame(in_flight)
+        in_flight = issued % 2
+        issued += 1
+    if in_flight is not None:
+        r.wait_frame(in_flight)
     torch.cuda.synchronize()
     sec = time.perf_counter() - t0
     tt = torch.tensor([sec], dtype=torch.float64, device="cuda")

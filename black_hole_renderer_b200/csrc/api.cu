@@ -99,6 +99,7 @@ extern "C" void bhr_destroy(bhr_ctx* ctx) {
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int k = 0; k < 6; ++k) if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
     for (int k = 0; k < 4; ++k) if (ctx->ent_ev[k]) cudaEventDestroy(ctx->ent_ev[k]);
+    for (int k = 0; k < 8; ++k) if (ctx->frame_ev[k]) cudaEventDestroy(ctx->frame_ev[k]);
     if (ctx->h_entities) cudaFreeHost(ctx->h_entities);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     free(ctx);
@@ -182,8 +183,7 @@ extern "C" int bhr_render_rows_stage2(bhr_ctx* ctx, uint32_t flags, int row0, in
     return BHR_OK;
 }
 
-extern "C" int bhr_render(bhr_ctx* ctx, const bhr_camera* cam, uint32_t flags, float* out_f32, uint8_t* out_u8) {
-    if (!ctx || !cam) return BHR_ERR_INVALID;
+static int render_enqueue(bhr_ctx* ctx, const bhr_camera* cam, uint32_t flags, float* out_f32, uint8_t* out_u8) {
     int rc = bhr_render_rows_stage1(ctx, cam, flags, 0, ctx->H);
     if (rc) return rc;
     double sums[3];
@@ -200,7 +200,30 @@ extern "C" int bhr_render(bhr_ctx* ctx, const bhr_camera* cam, uint32_t flags, f
     if (out_f32) BHR_CUDA(ctx, cudaMemcpyAsync(out_f32, ctx->final_f32, n3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     if (out_u8) BHR_CUDA(ctx, cudaMemcpyAsync(out_u8, ctx->final_u8, n3, cudaMemcpyDeviceToHost, ctx->stream));
     BHR_CUDA(ctx, cudaEventRecord(ctx->ev[5], ctx->stream));
+    return BHR_OK;
+}
+
+extern "C" int bhr_render(bhr_ctx* ctx, const bhr_camera* cam, uint32_t flags, float* out_f32, uint8_t* out_u8) {
+    if (!ctx || !cam) return BHR_ERR_INVALID;
+    int rc = render_enqueue(ctx, cam, flags, out_f32, out_u8);
+    if (rc) return rc;
     if (out_f32 || out_u8) BHR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return BHR_OK;
+}
+
+extern "C" int bhr_render_async(bhr_ctx* ctx, const bhr_camera* cam, uint32_t flags, float* out_f32, uint8_t* out_u8, int slot) {
+    if (!ctx || !cam || slot < 0 || slot >= 8) return BHR_ERR_INVALID;
+    int rc = render_enqueue(ctx, cam, flags, out_f32, out_u8);
+    if (rc) return rc;
+    if (!ctx->frame_ev[slot]) BHR_CUDA(ctx, cudaEventCreateWithFlags(&ctx->frame_ev[slot], cudaEventDisableTiming));
+    BHR_CUDA(ctx, cudaEventRecord(ctx->frame_ev[slot], ctx->stream));
+    return BHR_OK;
+}
+
+extern "C" int bhr_wait_frame(bhr_ctx* ctx, int slot) {
+    if (!ctx || slot < 0 || slot >= 8) return BHR_ERR_INVALID;
+    if (!ctx->frame_ev[slot]) BHR_FAIL(ctx, BHR_ERR_STATE, "no frame was enqueued in slot %d", slot);
+    BHR_CUDA(ctx, cudaEventSynchronize(ctx->frame_ev[slot]));
     return BHR_OK;
 }
 

@@ -85,6 +85,7 @@ struct bhr_ctx {
     void* stats_state;
 
     cudaEvent_t ev[6];
+    cudaEvent_t frame_ev[8];           // completion events of bhr_render_async slots
     int ev_valid;
     float tint[3];
 };

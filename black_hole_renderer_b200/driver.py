@@ -135,7 +135,6 @@ def render_video(renderer, width, height, n_frames, fps, output_path, fov, stati
     os.makedirs(temp_dir, exist_ok=True)
 
     pool = ThreadPoolExecutor(max_workers=int(os.environ.get("BHR_PNG_WORKERS", "2")))
-    pending = []
 
     def save_png(path, img_u8):
         Image.fromarray(img_u8, "RGB").save(path)
@@ -149,6 +148,20 @@ def render_video(renderer, width, height, n_frames, fps, output_path, fov, stati
         for f in range(max(completed) + 1):
             advance_lifecycle_frame(renderer, factories, f * dt, dt)
 
+    # Pipelined loop: frame i is enqueued without waiting (texture kernels, render, D2H into one of
+    # RING pinned buffers); while the device works on it the host waits for frame i - 1, hands its
+    # buffer to the PNG pool and runs the lifecycle tick / entity packing of frame i + 1.
+    RING = 6
+    bufs = [renderer.pinned_frame(np.uint8) for _ in range(RING)]
+    busy = [None] * RING                       # PNG job still reading the buffer
+    in_flight = None                           # (frame, slot) enqueued, not yet waited for
+
+    def retire(item):
+        frame_done, slot = item
+        renderer.wait_frame(slot)
+        busy[slot] = pool.submit(save_png, os.path.join(temp_dir, f"frame_{frame_done:04d}.png"), bufs[slot])
+        completed.add(frame_done)
+
     t_start = time.time()
     rendered = 0
     for frame in range(n_frames):
@@ -161,18 +174,24 @@ def render_video(renderer, width, height, n_frames, fps, output_path, fov, stati
             for f in factories.values():      # keep the RNG streams in step; no device work
                 f.tick(now=t, dt=dt)
             continue
+        slot = rendered % RING
+        if busy[slot] is not None:
+            busy[slot].result()
+            busy[slot] = None
         advance_lifecycle_frame(renderer, factories, t, dt, recompute_stats=(frame % STATS_PERIOD == 0))
-        img_u8 = renderer.render_u8(cam_pos, fov, frame=0)
+        renderer.render_u8_async(cam_pos, fov, bufs[slot], slot, frame=0)
+        if in_flight is not None:
+            retire(in_flight)
+        in_flight = (frame, slot)
         rendered += 1
-        if len(pending) >= 4:
-            pending.pop(0).result()
-        pending.append(pool.submit(save_png, os.path.join(temp_dir, f"frame_{frame:04d}.png"), img_u8))
-        completed.add(frame)
-        if rendered % 10 == 0 or frame == n_frames - 1:
+        if rendered % 10 == 0:
             with open(my_progress, "w") as f:
                 json.dump({"params": params, "completed": sorted(completed)}, f)
         if rendered % 100 == 0:
             print(f"  [rank {rank}] frame {frame}/{n_frames}, {rendered / (time.time() - t_start):.1f} frames/s")
+    if in_flight is not None:
+        retire(in_flight)
+    pending = [b for b in busy if b is not None]
     for f in pending:
         f.result()
     pool.shutdown(wait=True)

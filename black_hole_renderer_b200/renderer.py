@@ -246,6 +246,19 @@ class Renderer:
                                          out.ctypes.data))
         return out
 
+    def render_u8_async(self, cam_pos, fov, out, slot, frame=0, skip_differentials=False, skip_bloom=False):
+        """Enqueue a frame whose 8-bit result lands in the pinned array `out` (from
+        `pinned_frame(np.uint8)`); returns at once.  `wait_frame(slot)` blocks until it is there.
+        Video loops use it to overlap the host's lifecycle work with the device (driver.py)."""
+        cam = self._camera(cam_pos, fov, frame)
+        assert out.dtype == np.uint8 and out.flags.c_contiguous
+        self._check(self._lib.bhr_render_async(self._ctx, C.byref(cam),
+                                               self._flags(skip_differentials, skip_bloom), None,
+                                               out.ctypes.data, int(slot)))
+
+    def wait_frame(self, slot):
+        self._check(self._lib.bhr_wait_frame(self._ctx, int(slot)))
+
     def render_device(self, cam_pos, fov, frame=0, skip_differentials=False, skip_bloom=False,
                       aux=False):
         """Enqueue one frame and leave the results in device buffers (no host copy, no sync)."""

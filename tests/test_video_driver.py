@@ -18,9 +18,16 @@ class FakeRenderer:
     def recompute_interactive_stats(self): self.stats_calls += 1
     def compose_interactive_texture(self, solo_idx=-1): pass
 
-    def render_u8(self, cam_pos, fov, frame=0):
+    def pinned_frame(self, dtype=np.uint8):
+        return np.zeros((4, 8, 3), dtype=dtype)
+
+    def render_u8_async(self, cam_pos, fov, out, slot, frame=0):
         self.cams.append(list(cam_pos))
-        return np.zeros((4, 8, 3), dtype=np.uint8)
+        self.slots = getattr(self, "slots", []) + [slot]
+        out[...] = len(self.cams) % 251          # frame-dependent content: checks the buffer ring
+
+    def wait_frame(self, slot):
+        assert slot in self.slots
 
 
 def _run(tmp_path, renderer, n_frames=12, resume=False, rank=0, world=1, orbit=True, degrees=90.0):
@@ -44,6 +51,9 @@ def test_orbit_camera_path_and_files(tmp_path):
     assert sorted(p for p in os.listdir(d) if p.endswith(".png")) == [f"frame_{f:04d}.png" for f in range(12)]
     prog = json.load(open(d / "progress.json"))
     assert sorted(prog["completed"]) == list(range(12))
+    from PIL import Image
+    for f in range(12):     # every PNG holds its own frame although the pinned buffers are recycled
+        assert np.all(np.array(Image.open(d / f"frame_{f:04d}.png")) == (f + 1) % 251)
     assert prog["params"] == {"n_frames": 12, "fov": 90.0, "orbit": True, "disk_rotation_speed": 0.1,
                               "orbit_degrees": 90.0}
     # init (1) + frame 0 (frame % 60 == 0)
