@@ -100,6 +100,8 @@ extern "C" void bhr_destroy(bhr_ctx* ctx) {
     for (int k = 0; k < 6; ++k) if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
     for (int k = 0; k < 4; ++k) if (ctx->ent_ev[k]) cudaEventDestroy(ctx->ent_ev[k]);
     for (int k = 0; k < 8; ++k) if (ctx->frame_ev[k]) cudaEventDestroy(ctx->frame_ev[k]);
+    if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+    if (ctx->copy_done) cudaEventDestroy(ctx->copy_done);
     if (ctx->h_entities) cudaFreeHost(ctx->h_entities);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     free(ctx);
@@ -116,6 +118,7 @@ extern "C" int bhr_set_stream(bhr_ctx* ctx, void* cuda_stream) {
 extern "C" int bhr_synchronize(bhr_ctx* ctx) {
     if (!ctx) return BHR_ERR_INVALID;
     BHR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->copy_stream) BHR_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
     return BHR_OK;
 }
 
@@ -183,7 +186,11 @@ extern "C" int bhr_render_rows_stage2(bhr_ctx* ctx, uint32_t flags, int row0, in
     return BHR_OK;
 }
 
-static int render_enqueue(bhr_ctx* ctx, const bhr_camera* cam, uint32_t flags, float* out_f32, uint8_t* out_u8) {
+// copy_stream != nullptr: the D2H copies run on that stream (after the composite), so that the
+// next frame's kernels overlap them; the next composite waits for ctx->copy_done before it
+// overwrites the final buffers (post.cu).
+static int render_enqueue(bhr_ctx* ctx, const bhr_camera* cam, uint32_t flags, float* out_f32, uint8_t* out_u8,
+                          cudaStream_t copy_stream) {
     int rc = bhr_render_rows_stage1(ctx, cam, flags, 0, ctx->H);
     if (rc) return rc;
     double sums[3];
@@ -196,16 +203,26 @@ static int render_enqueue(bhr_ctx* ctx, const bhr_camera* cam, uint32_t flags, f
     }
     rc = bhr_render_rows_stage2(ctx, flags, 0, ctx->H, psums);
     if (rc) return rc;
-    const size_t n3 = (size_t)ctx->W * ctx->H * 3;
-    if (out_f32) BHR_CUDA(ctx, cudaMemcpyAsync(out_f32, ctx->final_f32, n3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-    if (out_u8) BHR_CUDA(ctx, cudaMemcpyAsync(out_u8, ctx->final_u8, n3, cudaMemcpyDeviceToHost, ctx->stream));
     BHR_CUDA(ctx, cudaEventRecord(ctx->ev[5], ctx->stream));
+    cudaStream_t cs = ctx->stream;
+    if (copy_stream && (out_f32 || out_u8)) {
+        cs = copy_stream;
+        BHR_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->ev[5], 0));
+    }
+    const size_t n3 = (size_t)ctx->W * ctx->H * 3;
+    if (out_f32) BHR_CUDA(ctx, cudaMemcpyAsync(out_f32, ctx->final_f32, n3 * sizeof(float), cudaMemcpyDeviceToHost, cs));
+    if (out_u8) BHR_CUDA(ctx, cudaMemcpyAsync(out_u8, ctx->final_u8, n3, cudaMemcpyDeviceToHost, cs));
+    if (cs != ctx->stream) {
+        if (!ctx->copy_done) BHR_CUDA(ctx, cudaEventCreateWithFlags(&ctx->copy_done, cudaEventDisableTiming));
+        BHR_CUDA(ctx, cudaEventRecord(ctx->copy_done, cs));
+        ctx->copy_pending = 1;
+    }
     return BHR_OK;
 }
 
 extern "C" int bhr_render(bhr_ctx* ctx, const bhr_camera* cam, uint32_t flags, float* out_f32, uint8_t* out_u8) {
     if (!ctx || !cam) return BHR_ERR_INVALID;
-    int rc = render_enqueue(ctx, cam, flags, out_f32, out_u8);
+    int rc = render_enqueue(ctx, cam, flags, out_f32, out_u8, nullptr);
     if (rc) return rc;
     if (out_f32 || out_u8) BHR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return BHR_OK;
@@ -213,10 +230,11 @@ extern "C" int bhr_render(bhr_ctx* ctx, const bhr_camera* cam, uint32_t flags, f
 
 extern "C" int bhr_render_async(bhr_ctx* ctx, const bhr_camera* cam, uint32_t flags, float* out_f32, uint8_t* out_u8, int slot) {
     if (!ctx || !cam || slot < 0 || slot >= 8) return BHR_ERR_INVALID;
-    int rc = render_enqueue(ctx, cam, flags, out_f32, out_u8);
+    if (!ctx->copy_stream) BHR_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    int rc = render_enqueue(ctx, cam, flags, out_f32, out_u8, ctx->copy_stream);
     if (rc) return rc;
     if (!ctx->frame_ev[slot]) BHR_CUDA(ctx, cudaEventCreateWithFlags(&ctx->frame_ev[slot], cudaEventDisableTiming));
-    BHR_CUDA(ctx, cudaEventRecord(ctx->frame_ev[slot], ctx->stream));
+    BHR_CUDA(ctx, cudaEventRecord(ctx->frame_ev[slot], (out_f32 || out_u8) ? ctx->copy_stream : ctx->stream));
     return BHR_OK;
 }
 

@@ -86,6 +86,8 @@ struct bhr_ctx {
 
     cudaEvent_t ev[6];
     cudaEvent_t frame_ev[8];           // completion events of bhr_render_async slots
+    cudaStream_t copy_stream;          // D2H of finished frames (bhr_render_async), overlaps the next frame
+    cudaEvent_t copy_done; int copy_pending;
     int ev_valid;
     float tint[3];
 };

@@ -436,6 +436,10 @@ int bhr_launch_bloom_v_composite(bhr_ctx* ctx, uint32_t flags, int row0, int row
                                                           ctx->d_wtab, ctx->wtab_stride, ctx->d_wsum_y, plane);
         BHR_CUDA(ctx, cudaGetLastError());
     }
+    if (ctx->copy_pending) {      // a frame is still being copied out of the final buffers (bhr_render_async)
+        BHR_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copy_done, 0));
+        ctx->copy_pending = 0;
+    }
     const int cgrid = 148 * 8;
 #define BHR_COMPOSITE(B, V, FL) composite_kernel<B, V, FL><<<cgrid, 256, 0, ctx->stream>>>( \
         ctx->bg, ctx->disk, ctx->blur, ctx->final_f32, ctx->final_u8, W, row0, row1, plane, F)

@@ -63,14 +63,37 @@ __constant__ unsigned char c_perm[256] = {
     29, 24, 72, 243, 141, 128, 195, 78, 66, 215, 61, 156, 180};
 
 // the kernels read the permutation from shared memory (divergent byte lookups: constant memory
-// would serialise them)
-struct Perm { const unsigned char* t; __device__ __forceinline__ int operator()(int i) const { return t[i & 255]; } };
+// would serialise them); t12[i] = t[i] % 12 serves the last lookup of each corner, whose result
+// is only used modulo 12 (render.py:2643)
+struct Perm {
+    const unsigned char* t;
+    const unsigned char* t12;
+    __device__ __forceinline__ int operator()(int i) const { return t[i & 255]; }
+    __device__ __forceinline__ int mod12(int i) const { return t12[i & 255]; }
+};
+__device__ __forceinline__ void load_perm(unsigned char* sperm /* [512] */, Perm& perm) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) { sperm[i] = c_perm[i]; sperm[256 + i] = c_perm[i] % 12; }
+    __syncthreads();
+    perm.t = sperm; perm.t12 = sperm + 256;
+}
 
-__device__ __forceinline__ float grad3_dot(int hash, float x, float y, float z) {
-    int h = hash % 12;
-    float u = h < 8 ? x : y;
-    float v = h < 4 ? y : z;      // the (h == 12 || h == 14) arm of render.py:2657 is unreachable
-    return ((h & 1) == 0 ? u : -u) + ((h & 2) == 0 ? v : -v);
+// gradient direction h in [0, 12): (+-u) + (+-v) with u = h < 8 ? x : y, v = h < 4 ? y : z
+// (the h == 12 / 14 arm of render.py:2657 is unreachable); negation = sign-bit flip
+__device__ __forceinline__ float grad3_dot(int h, float x, float y, float z) {
+    const float u = h < 8 ? x : y;
+    const float v = h < 4 ? y : z;
+    const float su = __uint_as_float(__float_as_uint(u) ^ ((unsigned)(h & 1) << 31));
+    const float sv = __uint_as_float(__float_as_uint(v) ^ ((unsigned)(h & 2) << 30));
+    return __fadd_rn(su, sv);
+}
+
+// one corner: t = 0.6 - x^2 - y^2 - z^2; contributes t^4 * grad when t >= 0.  Branch-free: a corner
+// outside the kernel adds +0.0f, which leaves the (never negative-zero) running sum unchanged.
+__device__ __forceinline__ float corner(float n, int h, float x, float y, float z) {
+    float t = __fsub_rn(__fsub_rn(__fsub_rn(0.6f, __fmul_rn(x, x)), __fmul_rn(y, y)), __fmul_rn(z, z));
+    const float t2 = __fmul_rn(t, t);
+    const float c = __fmul_rn(__fmul_rn(t2, t2), grad3_dot(h, x, y, z));
+    return __fadd_rn(n, t >= 0.0f ? c : 0.0f);
 }
 
 __device__ float simplex3(const Perm& perm, float x, float y, float z) {
@@ -83,33 +106,23 @@ __device__ float simplex3(const Perm& perm, float x, float y, float z) {
     int i = (int)fi, j = (int)fj, k = (int)fk;
     float t = __fmul_rn((float)(i + j + k), G3);
     float x0 = __fsub_rn(x, __fsub_rn(fi, t)), y0 = __fsub_rn(y, __fsub_rn(fj, t)), z0 = __fsub_rn(z, __fsub_rn(fk, t));
-    int i1, j1, k1, i2, j2, k2;
-    if (x0 >= y0) {
-        if (y0 >= z0) { i1 = 1; j1 = 0; k1 = 0; i2 = 1; j2 = 1; k2 = 0; }
-        else if (x0 >= z0) { i1 = 1; j1 = 0; k1 = 0; i2 = 1; j2 = 0; k2 = 1; }
-        else { i1 = 0; j1 = 0; k1 = 1; i2 = 1; j2 = 0; k2 = 1; }
-    } else {
-        if (y0 < z0) { i1 = 0; j1 = 0; k1 = 1; i2 = 0; j2 = 1; k2 = 1; }
-        else if (x0 < z0) { i1 = 0; j1 = 1; k1 = 0; i2 = 0; j2 = 1; k2 = 1; }
-        else { i1 = 0; j1 = 1; k1 = 0; i2 = 1; j2 = 1; k2 = 0; }
-    }
+    // simplex traversal order (render.py:2694-2712) as predicates of a = x0 >= y0, b = y0 >= z0, c = x0 >= z0
+    const bool a = x0 >= y0, b = y0 >= z0, c = x0 >= z0;
+    const int i1 = a && (b || c), j1 = !a && b, k1 = !b && !(a && c);
+    const int i2 = a || (b && c), j2 = b || !a, k2 = !b || (!a && !c);
     float x1 = __fadd_rn(__fsub_rn(x0, (float)i1), G3), y1 = __fadd_rn(__fsub_rn(y0, (float)j1), G3), z1 = __fadd_rn(__fsub_rn(z0, (float)k1), G3);
     float x2 = __fadd_rn(__fsub_rn(x0, (float)i2), G3x2), y2 = __fadd_rn(__fsub_rn(y0, (float)j2), G3x2), z2 = __fadd_rn(__fsub_rn(z0, (float)k2), G3x2);
     float x3 = __fadd_rn(__fsub_rn(x0, 1.0f), G3x3), y3 = __fadd_rn(__fsub_rn(y0, 1.0f), G3x3), z3 = __fadd_rn(__fsub_rn(z0, 1.0f), G3x3);
-    int ii = i & 255, jj = j & 255, kk = k & 255;
-    int gi0 = perm(ii + perm(jj + perm(kk)));
-    int gi1 = perm(ii + i1 + perm(jj + j1 + perm(kk + k1)));
-    int gi2 = perm(ii + i2 + perm(jj + j2 + perm(kk + k2)));
-    int gi3 = perm(ii + 1 + perm(jj + 1 + perm(kk + 1)));
+    const int ii = i & 255, jj = j & 255, kk = k & 255;
+    const int gi0 = perm.mod12(ii + perm(jj + perm(kk)));
+    const int gi1 = perm.mod12(ii + i1 + perm(jj + j1 + perm(kk + k1)));
+    const int gi2 = perm.mod12(ii + i2 + perm(jj + j2 + perm(kk + k2)));
+    const int gi3 = perm.mod12(ii + 1 + perm(jj + 1 + perm(kk + 1)));
     float n = 0.0f;
-    float t0 = __fsub_rn(__fsub_rn(__fsub_rn(0.6f, __fmul_rn(x0, x0)), __fmul_rn(y0, y0)), __fmul_rn(z0, z0));
-    if (t0 >= 0.0f) { t0 = __fmul_rn(t0, t0); n = __fadd_rn(n, __fmul_rn(__fmul_rn(t0, t0), grad3_dot(gi0, x0, y0, z0))); }
-    float t1 = __fsub_rn(__fsub_rn(__fsub_rn(0.6f, __fmul_rn(x1, x1)), __fmul_rn(y1, y1)), __fmul_rn(z1, z1));
-    if (t1 >= 0.0f) { t1 = __fmul_rn(t1, t1); n = __fadd_rn(n, __fmul_rn(__fmul_rn(t1, t1), grad3_dot(gi1, x1, y1, z1))); }
-    float t2 = __fsub_rn(__fsub_rn(__fsub_rn(0.6f, __fmul_rn(x2, x2)), __fmul_rn(y2, y2)), __fmul_rn(z2, z2));
-    if (t2 >= 0.0f) { t2 = __fmul_rn(t2, t2); n = __fadd_rn(n, __fmul_rn(__fmul_rn(t2, t2), grad3_dot(gi2, x2, y2, z2))); }
-    float t3 = __fsub_rn(__fsub_rn(__fsub_rn(0.6f, __fmul_rn(x3, x3)), __fmul_rn(y3, y3)), __fmul_rn(z3, z3));
-    if (t3 >= 0.0f) { t3 = __fmul_rn(t3, t3); n = __fadd_rn(n, __fmul_rn(__fmul_rn(t3, t3), grad3_dot(gi3, x3, y3, z3))); }
+    n = corner(n, gi0, x0, y0, z0);
+    n = corner(n, gi1, x1, y1, z1);
+    n = corner(n, gi2, x2, y2, z2);
+    n = corner(n, gi3, x3, y3, z3);
     return __fmul_rn(32.0f, n);
 }
 
@@ -131,10 +144,9 @@ __device__ __forceinline__ float a_(float a, float b) { return __fadd_rn(a, b); 
 
 __global__ void __launch_bounds__(256) noise_eval_kernel(const float* __restrict__ coords, int n, int mode, int octaves,
                                                          float persistence, float lacunarity, float* __restrict__ out) {
-    __shared__ unsigned char sperm[256];
-    sperm[threadIdx.x] = c_perm[threadIdx.x];
-    __syncthreads();
-    Perm perm{sperm};
+    __shared__ unsigned char sperm[512];
+    Perm perm;
+    load_perm(sperm, perm);
     int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= n) return;
     float x = coords[3 * i], y = coords[3 * i + 1], z = coords[3 * i + 2];
@@ -146,10 +158,9 @@ __global__ void __launch_bounds__(256) noise_eval_kernel(const float* __restrict
 // they are evaluated in double and rounded once (the oracle's ideal-libm convention).
 __global__ void __launch_bounds__(256) background_kernel(float* __restrict__ comp, int n_r, int n_phi, int az_freq,
                                                          float az_shear, float r_inner, float r_outer, float t) {
-    __shared__ unsigned char sperm[256];
-    sperm[threadIdx.x] = c_perm[threadIdx.x];
-    __syncthreads();
-    Perm perm{sperm};
+    __shared__ unsigned char sperm[512];
+    Perm perm;
+    load_perm(sperm, perm);
     const size_t plane = (size_t)n_r * n_phi;
     const size_t o = blockIdx.x * (size_t)256 + threadIdx.x;
     if (o >= plane) return;

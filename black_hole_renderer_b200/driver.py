@@ -134,10 +134,12 @@ def render_video(renderer, width, height, n_frames, fps, output_path, fov, stati
         barrier()
     os.makedirs(temp_dir, exist_ok=True)
 
-    pool = ThreadPoolExecutor(max_workers=int(os.environ.get("BHR_PNG_WORKERS", "2")))
+    # PNG encoding is host work outside the render path and the wall-clock limit of a video run
+    # (about 50 ms per 1080p frame and core at zlib level 1): use the host's cores for it
+    pool = ThreadPoolExecutor(max_workers=int(os.environ.get("BHR_PNG_WORKERS", str(min(16, os.cpu_count() or 2)))))
 
     def save_png(path, img_u8):
-        Image.fromarray(img_u8, "RGB").save(path)
+        Image.fromarray(img_u8, "RGB").save(path, compress_level=int(os.environ.get("BHR_PNG_LEVEL", "1")))
 
     n_r, n_phi = renderer.dtex_h, renderer.dtex_w
     factories = init_lifecycle_system(renderer, n_r, n_phi, seed=42)
@@ -151,7 +153,7 @@ def render_video(renderer, width, height, n_frames, fps, output_path, fov, stati
     # Pipelined loop: frame i is enqueued without waiting (texture kernels, render, D2H into one of
     # RING pinned buffers); while the device works on it the host waits for frame i - 1, hands its
     # buffer to the PNG pool and runs the lifecycle tick / entity packing of frame i + 1.
-    RING = 6
+    RING = 8
     bufs = [renderer.pinned_frame(np.uint8) for _ in range(RING)]
     busy = [None] * RING                       # PNG job still reading the buffer
     in_flight = None                           # (frame, slot) enqueued, not yet waited for
