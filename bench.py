@@ -136,6 +136,27 @@ def orbit_video_block(r, n_r, n_phi, rank, world, dist, torch, block=60, n_frame
             "excludes": "PNG / x264 encoding (host I/O)", "sharding": f"{block}-frame blocks round-robin, no collective"}
 
 
+def profiled_traffic():
+    """DRAM bytes per launch of the dominant kernel from the newest committed `ncu --set full`
+    capture (profiles/*_raymarch_ncu.txt: dram__bytes_read.sum + dram__bytes_write.sum)."""
+    import glob
+    import re
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_raymarch_ncu.txt")), reverse=True):
+        blocks = open(path).read().split("=====")
+        for b in blocks:
+            if "raymarch_persistent<0" not in b:
+                continue
+            tot = 0.0
+            for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                m = re.search(re.escape(name) + r" \[(\w+)\] = ([0-9.]+)", b)
+                if not m:
+                    break
+                tot += float(m.group(2)) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[m.group(1)]
+            else:
+                return tot, os.path.relpath(path, ROOT)
+    return None, None
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU path (oracle port, all host threads)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -281,6 +302,7 @@ def main():
     rays = W * H * world
     flops = FLOP_PER_STEP * total_steps
     achieved = flops / (stage["ray_march"] * 1e-3) / 1e12
+    traffic, traffic_src = profiled_traffic()
     line = {
         "metric": "Mrays/s", "value": rays / (ms_step * 1e-3) / 1e6, "unit": "Mrays/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
@@ -300,7 +322,9 @@ def main():
                 "note": "Renderer.render(cam, fov, out=pinned (H,W,3) f32): camera struct H2D, frame D2H, host sync"},
         "gpu_launches": 6 * args.steps * world,   # band_list, raymarch_persistent, retrace, bloom_h, bloom_v, composite per frame
         "roofline": {"bound": "fp32", "kernel": "raymarch_persistent (+ band_list, retrace)", "achieved": achieved, "peak": peak,
-                     "unit": "TFLOP/s", "frac": (achieved / peak) if peak else None, "traffic": None,
+                     "unit": "TFLOP/s", "frac": (achieved / peak) if peak else None, "traffic": traffic,
+                     "traffic_note": (f"dram read + write bytes per launch from {traffic_src} (ncu --set full); the kernel is "
+                                      "FP32-bound, its algorithmic DRAM traffic is the two 24.9 MB layers it writes") if traffic else None,
                      "algorithmic": f"{FLOP_PER_STEP} flop/RK4 step x {total_steps} steps (SURVEY.md 8d)",
                      "peak_source": "scalar FFMA microbenchmark measured in this run (bhr_measure_fp32_peak); "
                                     "MEASURED_PEAKS.json holds no FP32 figure"},
