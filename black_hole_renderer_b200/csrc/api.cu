@@ -71,6 +71,7 @@ extern "C" int bhr_create(const bhr_config* cfg, bhr_ctx** out) {
     ctx->d_total_steps = (unsigned long long*)(ctx->d_queue_count + 4);
     ctx->retrace_min_cross = 3;
     ctx->retrace_band = 0.02f;
+    ctx->band_lo_auto = 1;
     CREATE_CHECK(cudaMemset(ctx->bg, 0, plane * 3 * sizeof(float)));
     CREATE_CHECK(cudaMemset(ctx->disk, 0, plane * 3 * sizeof(float)));
     CREATE_CHECK(cudaMemset(ctx->hblur, 0, plane * 3 * sizeof(float)));
@@ -134,6 +135,7 @@ extern "C" int bhr_set_option(bhr_ctx* ctx, const char* key, double value) {
     if (ctx && !strcmp(key, "retrace_min_cross")) { ctx->retrace_min_cross = (int)value; return BHR_OK; }
     if (ctx && !strcmp(key, "retrace_band")) { ctx->retrace_band = (float)value; return BHR_OK; }
     if (ctx && !strcmp(key, "persistent")) { ctx->persistent = (int)value; return BHR_OK; }
+    if (ctx && !strcmp(key, "band_lo_auto")) { ctx->band_lo_auto = (int)value; return BHR_OK; }
     if (ctx && !strcmp(key, "pblock_big")) { ctx->pblock_big = (int)value; return BHR_OK; }
     if (ctx) snprintf(ctx->err, sizeof(ctx->err), "unknown option %s", key);
     return BHR_ERR_INVALID;

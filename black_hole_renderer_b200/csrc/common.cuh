@@ -41,7 +41,8 @@ struct RayParams {
     unsigned int* queue_count;  // tail: entries appended so far
     unsigned int queue_serial;  // tags the entries of this launch
     int retrace_min_cross;
-    float retrace_band;         // |b / b_crit - 1| below which a ray is traced by the strict integrator
+    float retrace_band;         // rays with band_lo < b / b_crit - 1 < retrace_band go to the strict integrator
+    float band_lo;              // (negative) lower edge, see bhr_launch_raymarch
     float inv_rcam3;            // 1 / |cam|^3
     int* band;                  // persistent kernel: pixels of the ill-conditioned band (built beforehand)
     unsigned int* band_count;
@@ -65,7 +66,7 @@ struct bhr_ctx {
     uint8_t* final_u8;                 // (H, W, 3)
     uint8_t* cls; int* steps;
     unsigned long long* d_total_steps;
-    unsigned long long* retrace_queue; unsigned int* d_queue_count; int retrace_min_cross; unsigned int queue_serial; float retrace_band; int persistent, num_sms, pblock_big;
+    unsigned long long* retrace_queue; unsigned int* d_queue_count; int retrace_min_cross; unsigned int queue_serial; float retrace_band; int persistent, num_sms, pblock_big, band_lo_auto;
     double* d_flare_sums;              // {sum B, sum x*B, sum y*B}
 
     int bloom_R; float sigma_scale;

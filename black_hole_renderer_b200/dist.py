@@ -100,12 +100,13 @@ def device_tensor(renderer, buf_id, shape, dtype=torch.float32):
 
 
 def render_tiled(renderer, cam_pos, fov, frame=0, skip_differentials=False, skip_bloom=False,
-                 rank=0, world_size=1, group=None, want_u8=False):
+                 rank=0, world_size=1, group=None, want_u8=False, copy=True):
     """One frame split into row tiles over `world_size` GPUs (render.py:3865-3923 semantics).
 
     stage 1 (ray march + horizontal bloom pass on my rows) -> halo exchange of the H-blurred layer
     -> all-reduce of the flare sums -> stage 2 (vertical pass + composite + flare on my rows)
-    -> gather on rank 0.  Returns the (H, W, 3) frame (numpy) on rank 0, None elsewhere.
+    -> gather on rank 0.  Returns the (H, W, 3) frame (numpy) on rank 0, None elsewhere; with
+    copy=False the array aliases a per-renderer pinned buffer that the next call overwrites.
     """
     import ctypes as C
     H, W = renderer.height, renderer.width
@@ -139,4 +140,11 @@ def render_tiled(renderer, cam_pos, fov, frame=0, skip_differentials=False, skip
     frame_t = gather_rows(full[row0:row1], H, rank, world_size, 0, group)
     if frame_t is None:
         return None
-    return frame_t.cpu().numpy()
+    # page-locked landing buffer (cached per renderer and dtype): the D2H copy runs at PCIe speed
+    cache = renderer.__dict__.setdefault("_tiled_host", {})
+    host = cache.get(frame_t.dtype)
+    if host is None or host.shape != frame_t.shape:
+        host = cache[frame_t.dtype] = torch.empty(frame_t.shape, dtype=frame_t.dtype, pin_memory=True)
+    host.copy_(frame_t, non_blocking=True)
+    torch.cuda.current_stream(renderer.cuda_device).synchronize()
+    return host.numpy().copy() if copy else host.numpy()     # copy=False: valid until the next call

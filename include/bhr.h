@@ -91,7 +91,9 @@ int bhr_version(void);
  * 2 strict (reference operation order, exactly rounded; ~3x slower); "retrace_band" = eps: rays
  * whose impact parameter is within eps of the critical one (photon-ring rays, chaotic) are traced
  * by the strict integrator (default 0.02, 0 = off); "retrace_min_cross" = n: safety net, rays with
- * >= n disk-plane crossings are re-traced too (default 3, 0 = off); "persistent" = 1 (default):
+ * >= n disk-plane crossings are re-traced too (default 3, 0 = off); "band_lo_auto" = 1 (default): with the
+ * disk's inner edge outside the photon sphere the band is (-0.005, eps) -- rays safely below the
+ * critical impact parameter end in the horizon whatever they do near it; "persistent" = 1 (default):
  * one block per SM with work queues, strict and fast rays on disjoint SMs; "pblock_big" */
 int bhr_set_option(bhr_ctx* ctx, const char* key, double value);
 /* pinned host memory so that frame read-back DMA needs no staging copy */

@@ -12,7 +12,7 @@ def run(res, pov, fov, **kw):
     W, H = RESOLUTIONS[res] if isinstance(res, str) else res
     n_phi, n_r = O.disk_texture_resolution(W, H, pov, fov, kw.get("r_disk_inner", 2.0), kw.get("r_disk_outer", 15.0))
     sky = synthetic_skybox(); tex = synthetic_disk_texture(n_r, n_phi)
-    r = Renderer(W, H, sky, tex, **kw); r.set_option("raymarch_mode", 0); r.set_option("retrace_min_cross", int(os.environ.get("MINCROSS", "0"))); r.set_option("retrace_band", float(os.environ.get("BAND", "0.02")))
+    r = Renderer(W, H, sky, tex, **kw); r.set_option("raymarch_mode", 0); r.set_option("retrace_min_cross", int(os.environ.get("MINCROSS", "0"))); r.set_option("retrace_band", float(os.environ.get("BAND", "0.02"))); r.set_option("band_lo_auto", int(os.environ.get("LOAUTO", "1")))
     img = r.render(pov, fov, aux=True, skip_bloom=True); cls, steps = r.last_aux()
     okw = dict(step_size=kw.get("step_size", 0.1), r_max=kw.get("r_max", 10.0), r_inner=kw.get("r_disk_inner", 2.0),
                r_outer=kw.get("r_disk_outer", 15.0), disk_tilt=kw.get("disk_tilt", 0.0))
