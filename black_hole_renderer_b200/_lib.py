@@ -9,6 +9,7 @@ LIB_PATH = os.path.join(_HERE, "libbhr.so")
 BHR_SKIP_DIFFERENTIALS = 1
 BHR_SKIP_BLOOM = 2
 BHR_WANT_AUX = 4
+SKIP_FLARE = BHR_SKIP_FLARE = 8
 
 (BUF_BG, BUF_DISK, BUF_HBLUR, BUF_FINAL, BUF_FINAL_U8, BUF_CLASS, BUF_STEPS, BUF_DISK_TEX,
  BUF_DISK_MIPS, BUF_COMP, BUF_BLUR) = range(11)

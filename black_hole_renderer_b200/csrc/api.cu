@@ -197,7 +197,7 @@ static int render_enqueue(bhr_ctx* ctx, const bhr_camera* cam, uint32_t flags, f
     if (rc) return rc;
     double sums[3];
     const double* psums = nullptr;
-    if (ctx->cfg.lens_flare) {
+    if (ctx->cfg.lens_flare && !(flags & BHR_SKIP_FLARE)) {
         // the flare needs the global brightness centroid before any pixel can be finished
         rc = bhr_flare_sums(ctx, 0, ctx->H, sums);
         if (rc) return rc;

@@ -125,7 +125,9 @@ class Renderer:
         self.image_field = _Field(lambda: self._planar(L.BUF_BG).transpose(2, 1, 0).copy())
         self.disk_layer_field = _Field(lambda: self._planar(L.BUF_DISK).transpose(2, 1, 0).copy())
         self.blur_field = _Field(lambda: self._planar(L.BUF_BLUR).transpose(2, 1, 0).copy())
-        self.final_field = _Field(lambda: self._download(L.BUF_FINAL, (H, W, 3), np.float32)
+        # final_field[i, j] = frame[H - 1 - j, i]: (W, H, 3) with the y axis flipped for ti.GUI
+        # (_compose_final_kernel, render.py:3285-3300); filled by render_to_field
+        self.final_field = _Field(lambda: self._download(L.BUF_FINAL, (H, W, 3), np.float32)[::-1]
                                   .transpose(1, 0, 2).copy())
         self.disk_texture_field = _Field(
             lambda: self._download(L.BUF_DISK_TEX, (self.dtex_h, self.dtex_w, 4), np.float32))
@@ -265,6 +267,14 @@ class Renderer:
         cam = self._camera(cam_pos, fov, frame)
         self._check(self._lib.bhr_render(self._ctx, C.byref(cam),
                                          self._flags(skip_differentials, skip_bloom, aux), None, None))
+
+    def render_to_field(self, cam_pos, fov, frame=0, skip_differentials=False, skip_bloom=False):
+        """render_to_field (render.py:3819-3863): the frame stays on the device (no host copy, no
+        synchronisation, no lens flare); `final_field.to_numpy()` reads it back in the reference's
+        (W, H, 3), y-flipped layout."""
+        cam = self._camera(cam_pos, fov, frame)
+        self._check(self._lib.bhr_render(self._ctx, C.byref(cam),
+                                         self._flags(skip_differentials, skip_bloom) | L.SKIP_FLARE, None, None))
 
     def pinned_frame(self, dtype=np.float32):
         """A page-locked (H, W, 3) array for `render(..., out=)` / `render_u8(..., out=)`."""

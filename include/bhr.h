@@ -63,6 +63,7 @@ typedef struct {
 #define BHR_SKIP_DIFFERENTIALS 1u   /* render(skip_differentials=True), render.py:3900 */
 #define BHR_SKIP_BLOOM 2u           /* render(skip_bloom=True), render.py:3911         */
 #define BHR_WANT_AUX 4u             /* also fill the class / step-count buffers        */
+#define BHR_SKIP_FLARE 8u           /* render_to_field (render.py:3819-3863) never applies the lens flare */
 
 /* device buffers that can be inspected / exchanged (bhr_buffer, bhr_download) */
 typedef enum {

@@ -269,3 +269,16 @@ def test_strict_div6_is_the_ieee_division_on_every_float():
     # the only inputs that may differ are those whose quotient is subnormal (|x| < 6 * 2^-126);
     # positions / directions of a ray never get there
     assert total.value < 2 * 6 * 2 ** 23 + 16
+
+
+def test_render_to_field_layout():
+    """render_to_field (render.py:3819-3863): final_field is (W, H, 3), y-flipped, without flare."""
+    r, sky, tex, pov, fov, W, H = _scene((160, 90), lens_flare=True)
+    r.lens_flare = False
+    want = r.render(pov, fov)
+    r.lens_flare = True
+    r.render_to_field(pov, fov)
+    got = r.final_field.to_numpy()
+    assert got.shape == (W, H, 3)
+    assert np.array_equal(got, want[::-1].transpose(1, 0, 2))
+    assert not np.array_equal(r.render(pov, fov), want)        # (the flare is on for render())
