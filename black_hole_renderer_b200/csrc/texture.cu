@@ -66,30 +66,38 @@ __constant__ unsigned char c_perm[256] = {
 // would serialise them); t12[i] = t[i] % 12 serves the last lookup of each corner, whose result
 // is only used modulo 12 (render.py:2643)
 struct Perm {
-    const unsigned char* t;
-    const unsigned char* t12;
-    __device__ __forceinline__ int operator()(int i) const { return t[i & 255]; }
-    __device__ __forceinline__ int mod12(int i) const { return t12[i & 255]; }
+    const unsigned char* t;      // 512 entries: the table twice, so ii + i1 + perm(...) <= 511 needs no mask (render.py:2269-2288)
+    const float4* g;             // 512 entries: gradient direction of t[i] % 12 as (gx, gy, gz, 0), components in {-1, 0, 1}
+    __device__ __forceinline__ int operator()(int i) const { return t[i]; }
 };
-__device__ __forceinline__ void load_perm(unsigned char* sperm /* [512] */, Perm& perm) {
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) { sperm[i] = c_perm[i]; sperm[256 + i] = c_perm[i] % 12; }
+constexpr int kPermSmem = 512 + 512 * 16;     // bytes
+// gradient direction h in [0, 12): (+-u) + (+-v) with u = h < 8 ? x : y, v = h < 4 ? y : z and the
+// signs from bits 0 / 1 of h (render.py:2642-2660; the h == 12 / 14 arm is unreachable)
+__device__ __forceinline__ float4 grad_of(int h) {
+    const float su = (h & 1) ? -1.0f : 1.0f, sv = (h & 2) ? -1.0f : 1.0f;
+    if (h < 4) return make_float4(su, sv, 0.0f, 0.0f);
+    if (h < 8) return make_float4(su, 0.0f, sv, 0.0f);
+    return make_float4(0.0f, su, sv, 0.0f);
+}
+__device__ __forceinline__ void load_perm(unsigned char* smem /* kPermSmem bytes, 16-byte aligned */, Perm& perm) {
+    float4* g = reinterpret_cast<float4*>(smem);
+    unsigned char* t = smem + 512 * 16;
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) { t[i] = c_perm[i & 255]; g[i] = grad_of(c_perm[i & 255] % 12); }
     __syncthreads();
-    perm.t = sperm; perm.t12 = sperm + 256;
+    perm.t = t; perm.g = g;
 }
 
-// gradient direction h in [0, 12): (+-u) + (+-v) with u = h < 8 ? x : y, v = h < 4 ? y : z
-// (the h == 12 / 14 arm of render.py:2657 is unreachable); negation = sign-bit flip
-__device__ __forceinline__ float grad3_dot(int h, float x, float y, float z) {
-    const float u = h < 8 ? x : y;
-    const float v = h < 4 ? y : z;
-    const float su = __uint_as_float(__float_as_uint(u) ^ ((unsigned)(h & 1) << 31));
-    const float sv = __uint_as_float(__float_as_uint(v) ^ ((unsigned)(h & 2) << 30));
-    return __fadd_rn(su, sv);
+// The gradient dot product as gx x + gy y + gz z (left to right) with the tabulated direction:
+// multiplying by +-1 is a sign flip and the one zero term adds +-0, so this is (+-u) + (+-v)
+// exactly (up to the sign of an exact zero) -- on the FMA pipe instead of ~10 select / logic
+// instructions on the half-rate ALU pipe, which is this kernel's bottleneck.
+__device__ __forceinline__ float grad3_dot(const float4 g, float x, float y, float z) {
+    return __fadd_rn(__fadd_rn(__fmul_rn(g.x, x), __fmul_rn(g.y, y)), __fmul_rn(g.z, z));
 }
 
 // one corner: t = 0.6 - x^2 - y^2 - z^2; contributes t^4 * grad when t >= 0.  Branch-free: a corner
 // outside the kernel adds +0.0f, which leaves the (never negative-zero) running sum unchanged.
-__device__ __forceinline__ float corner(float n, int h, float x, float y, float z) {
+__device__ __forceinline__ float corner(float n, const float4 h, float x, float y, float z) {
     float t = __fsub_rn(__fsub_rn(__fsub_rn(0.6f, __fmul_rn(x, x)), __fmul_rn(y, y)), __fmul_rn(z, z));
     const float t2 = __fmul_rn(t, t);
     const float c = __fmul_rn(__fmul_rn(t2, t2), grad3_dot(h, x, y, z));
@@ -114,10 +122,10 @@ __device__ float simplex3(const Perm& perm, float x, float y, float z) {
     float x2 = __fadd_rn(__fsub_rn(x0, (float)i2), G3x2), y2 = __fadd_rn(__fsub_rn(y0, (float)j2), G3x2), z2 = __fadd_rn(__fsub_rn(z0, (float)k2), G3x2);
     float x3 = __fadd_rn(__fsub_rn(x0, 1.0f), G3x3), y3 = __fadd_rn(__fsub_rn(y0, 1.0f), G3x3), z3 = __fadd_rn(__fsub_rn(z0, 1.0f), G3x3);
     const int ii = i & 255, jj = j & 255, kk = k & 255;
-    const int gi0 = perm.mod12(ii + perm(jj + perm(kk)));
-    const int gi1 = perm.mod12(ii + i1 + perm(jj + j1 + perm(kk + k1)));
-    const int gi2 = perm.mod12(ii + i2 + perm(jj + j2 + perm(kk + k2)));
-    const int gi3 = perm.mod12(ii + 1 + perm(jj + 1 + perm(kk + 1)));
+    const float4 gi0 = perm.g[ii + perm(jj + perm(kk))];
+    const float4 gi1 = perm.g[ii + i1 + perm(jj + j1 + perm(kk + k1))];
+    const float4 gi2 = perm.g[ii + i2 + perm(jj + j2 + perm(kk + k2))];
+    const float4 gi3 = perm.g[ii + 1 + perm(jj + 1 + perm(kk + 1))];
     float n = 0.0f;
     n = corner(n, gi0, x0, y0, z0);
     n = corner(n, gi1, x1, y1, z1);
@@ -144,7 +152,7 @@ __device__ __forceinline__ float a_(float a, float b) { return __fadd_rn(a, b); 
 
 __global__ void __launch_bounds__(256) noise_eval_kernel(const float* __restrict__ coords, int n, int mode, int octaves,
                                                          float persistence, float lacunarity, float* __restrict__ out) {
-    __shared__ unsigned char sperm[512];
+    __shared__ __align__(16) unsigned char sperm[kPermSmem];
     Perm perm;
     load_perm(sperm, perm);
     int i = blockIdx.x * 256 + threadIdx.x;
@@ -158,21 +166,30 @@ __global__ void __launch_bounds__(256) noise_eval_kernel(const float* __restrict
 // they are evaluated in double and rounded once (the oracle's ideal-libm convention).
 __global__ void __launch_bounds__(256) background_kernel(float* __restrict__ comp, int n_r, int n_phi, int az_freq,
                                                          float az_shear, float r_inner, float r_outer, float t) {
-    __shared__ unsigned char sperm[512];
+    __shared__ __align__(16) unsigned char sperm[kPermSmem];
     Perm perm;
     load_perm(sperm, perm);
     const size_t plane = (size_t)n_r * n_phi;
-    const size_t o = blockIdx.x * (size_t)256 + threadIdx.x;
-    if (o >= plane) return;
-    const int ri = (int)(o / n_phi), pi = (int)(o % n_phi);
+    // block = 256 columns of row blockIdx.y; the quantities that depend on the row only (two
+    // double-precision pow, omega) are evaluated by one thread and shared
+    __shared__ float row_decay, row_shear, row_omega;
+    const int ri = blockIdx.y, pi = blockIdx.x * blockDim.x + threadIdx.x;
     const float r = __fdiv_rn((float)ri, (float)n_r);
+    if (threadIdx.x == 0) {
+        const float r_phys = a_(r_inner, m_(__fsub_rn(r_outer, r_inner), r));
+        row_omega = __fsqrt_rn(__fdiv_rn(0.5f, a_(m_(m_(r_phys, r_phys), r_phys), 1e-6f)));
+        row_decay = (float)pow((double)fmaxf(__fsub_rn(1.0f, r), 0.0f), (double)1.3f);
+        row_shear = m_((float)pow((double)r, (double)1.2f), az_shear);
+    }
+    __syncthreads();
+    if (pi >= n_phi) return;
+    const size_t o = (size_t)ri * n_phi + pi;
     const float phi = m_(__fdiv_rn((float)pi, (float)n_phi), 6.2831855f);
-    const float r_phys = a_(r_inner, m_(__fsub_rn(r_outer, r_inner), r));
-    const float omega = __fsqrt_rn(__fdiv_rn(0.5f, a_(m_(m_(r_phys, r_phys), r_phys), 1e-6f)));
+    const float omega = row_omega;
     const float phi_rot = a_(phi, m_(omega, t));
     const float cx = (float)cos((double)phi_rot), cy = (float)sin((double)phi_rot);
 
-    float decay = (float)pow((double)fmaxf(__fsub_rn(1.0f, r), 0.0f), (double)1.3f);
+    const float decay = row_decay;
     float tb = unit_fbm(perm, m_(cx, 8.0f), m_(cy, 8.0f), a_(m_(r, 8.0f), m_(t, 0.05f)), 4, 0.6f);
     comp[0 * plane + o] = m_(m_(decay, a_(0.85f, m_(0.15f, tb))), 0.25f);
     comp[1 * plane + o] = 0.0f;
@@ -188,7 +205,7 @@ __global__ void __launch_bounds__(256) background_kernel(float* __restrict__ com
     comp[3 * plane + o] = turb;
     comp[4 * plane + o] = m_(0.05f, turb);
 
-    float shear = m_((float)pow((double)r, (double)1.2f), az_shear);
+    const float shear = row_shear;
     float az_wave = a_(0.5f, m_(0.5f, (float)sin((double)m_(a_(phi_rot, shear), (float)az_freq))));
     float az_n = unit_fbm(perm, m_(cx, 3.0f), m_(cy, 3.0f), a_(m_(r, 3.0f), m_(t, 0.04f)), 3, 0.5f);
     comp[11 * plane + o] = m_(az_wave, az_n);
@@ -477,8 +494,14 @@ extern "C" int bhr_init_background(bhr_ctx* ctx, int n_r, int n_phi, int az_freq
 extern "C" int bhr_generate_background(bhr_ctx* ctx, float t) {
     if (!ctx) return BHR_ERR_INVALID;
     if (!ctx->bg_ready) BHR_FAIL(ctx, BHR_ERR_STATE, "Must call init_background_layer() first");
-    const size_t plane = (size_t)ctx->n_r * ctx->n_phi;
-    background_kernel<<<(unsigned)((plane + 255) / 256), 256, 0, ctx->stream>>>(
+    // one block per (row, column chunk); the block width that wastes the fewest lanes on the ragged
+    // last chunk (n_phi is a multiple of 16: 2912 = 13 x 224)
+    int best = 256, best_waste = 1 << 30;
+    for (int b = 256; b >= 128; b -= 32) {
+        const int waste = bhr_div_up(ctx->n_phi, b) * b - ctx->n_phi;
+        if (waste < best_waste) { best_waste = waste; best = b; }
+    }
+    background_kernel<<<dim3(bhr_div_up(ctx->n_phi, best), ctx->n_r), best, 0, ctx->stream>>>(
         ctx->comp, ctx->n_r, ctx->n_phi, ctx->az_freq, ctx->az_shear, ctx->cfg.r_disk_inner, ctx->cfg.r_disk_outer, t);
     BHR_CUDA(ctx, cudaGetLastError());
     return BHR_OK;
