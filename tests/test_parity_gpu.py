@@ -282,3 +282,26 @@ def test_render_to_field_layout():
     assert got.shape == (W, H, 3)
     assert np.array_equal(got, want[::-1].transpose(1, 0, 2))
     assert not np.array_equal(r.render(pov, fov), want)        # (the flare is on for render())
+
+
+def test_async_frames_equal_synchronous_frames():
+    """bhr_render_async / bhr_wait_frame: a ring of pinned buffers filled without waiting holds the
+    same frames as the synchronous call (the D2H copies run on the copy stream while the next frame
+    is traced)."""
+    from black_hole_renderer_b200.driver import orbit_camera
+    r, sky, tex, pov, fov, W, H = _scene((320, 180))
+    cams = [orbit_camera(pov, f, 36, 360.0) for f in range(6)]
+    want = [r.render_u8(c, fov).copy() for c in cams]
+    bufs = [r.pinned_frame(np.uint8) for _ in range(3)]
+    got = []
+    for i, c in enumerate(cams):
+        slot = i % 3
+        if i >= 3:                       # the buffer is about to be reused: retire its frame first
+            r.wait_frame(slot)
+            got.append(bufs[slot].copy())
+        r.render_u8_async(c, fov, bufs[slot], slot)
+    for i in range(3, 6):
+        r.wait_frame(i % 3)
+        got.append(bufs[i % 3].copy())
+    assert all(np.array_equal(a, b) for a, b in zip(got, want))
+    assert not np.array_equal(want[0], want[3])

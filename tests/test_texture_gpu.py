@@ -148,3 +148,28 @@ def test_compose_against_oracle():
     got = r.disk_texture_field.to_numpy()
     assert np.abs(got - want).max() <= 2e-5
     assert np.abs(r.disk_mips_field.to_numpy() - O.build_mips(got, 5, numpy_order=False)).max() <= 1e-7
+
+
+@pytest.mark.parametrize("case", ["ties", "no_structure", "negative", "fhd_texture"])
+def test_device_statistics_equal_numpy_on_hard_inputs(case):
+    """recompute_interactive_stats on the device (radix select + row sort + numpy's interpolation
+    on the exact order statistics) against the numpy restatement, bit for bit: heavy ties, no
+    positive structure at all (scale falls back to 1.0), negative values, the fhd texture size."""
+    import ctypes as C
+    n_r, n_phi = (416, 2912) if case == "fhd_texture" else (48, 208)
+    r = _renderer(n_r, n_phi)
+    r.init_background_layer(n_r, n_phi, seed=5)
+    rng = np.random.default_rng(7)
+    comp = rng.random((13, n_r, n_phi)).astype(np.float32)
+    if case == "ties":
+        comp = (np.round(comp * 4) / 4).astype(np.float32)         # five distinct values per plane
+    if case == "no_structure":
+        comp[[2, 4, 6, 8, 10]] = 0.0
+    if case == "negative":
+        comp[[2, 4, 6, 8, 10]] -= 0.45                               # structure sums of both signs
+        comp[1] -= 0.5
+    r._check(r._lib.bhr_upload_comp(r._ctx, comp.ctypes.data_as(C.POINTER(C.c_float))))
+    r.recompute_interactive_stats()
+    s, rs = O.interactive_stats(comp, r._bg_edge_np)
+    assert np.array_equal(s, r._param_stats_field.to_numpy()), (s, r._param_stats_field.to_numpy())
+    assert np.array_equal(rs, r._param_row_stats_field.to_numpy())
