@@ -366,6 +366,18 @@ class Renderer:
         device returns the exact order statistics on both sides of each quantile's virtual index
         (radix select / per-row sort, csrc/stats.cu) and `numpy_linear_lerp` applies numpy's own
         float32 interpolation to them -- the same numbers without the 63 MB read-back."""
+        p98, scale, row_max, row_p70, tb_max = self._device_stats()
+        p98, scale = max(p98, 0.01), max(scale, 0.01)
+        row_max = np.maximum(row_max, tb_max)
+        row_p70 = np.maximum(row_p70, tb_max * 0.8)
+        self._stats = np.array([p98, scale], dtype=np.float32)
+        self._row_stats = np.column_stack([row_max, row_p70]).astype(np.float32)
+        self._push_stats()
+
+    def _device_stats(self, floor_scale=True):
+        """(p98 of the density mix, p95 of the positive structure temperature, per-row max and
+        70 % quantile of the scaled structure, per-row max of the base temperature) of the current
+        component field, numpy's numbers from device order statistics (csrc/stats.cu)."""
         n_tot, n_pos = C.c_uint64(), C.c_uint64()
         self._check(self._lib.bhr_stats_prepare(self._ctx, int(self._param_enable_rt),
                                                 C.byref(n_tot), C.byref(n_pos)))
@@ -376,22 +388,55 @@ class Renderer:
         self._check(self._lib.bhr_stats_select(self._ctx, lo_d, lo_s, _fp(vals)))
         d_hi = vals[1] if hi_d != lo_d else vals[0]
         s_hi = vals[3] if hi_s != lo_s else vals[2]
-        p98 = max(float(numpy_linear_lerp(vals[0], d_hi, g_d)), 0.01)
+        p98 = float(numpy_linear_lerp(vals[0], d_hi, g_d))
         scale = float(numpy_linear_lerp(vals[2], s_hi, g_s)) if n_pos > 0 else 1.0
-        scale = max(scale, 0.01)
         # struct / (scale + 1e-6) * 0.8: the Python-float divisor becomes a float32 operand
-        denom = np.float32(scale + 1e-6)
+        denom = np.float32((max(scale, 0.01) if floor_scale else scale) + 1e-6)
         lo_r, hi_r, g_r = numpy_quantile_neighbours(self.dtex_w, np.asanyarray(0.7, dtype=np.float32))
         rows = np.zeros((self.dtex_h, 4), dtype=np.float32)
         self._check(self._lib.bhr_stats_rows(self._ctx, float(denom), lo_r, hi_r, _fp(rows)))
-        row_max = rows[:, 0]
         row_p70 = numpy_linear_lerp(rows[:, 1], rows[:, 2], g_r).astype(np.float32)
-        tb_max = rows[:, 3]
-        row_max = np.maximum(row_max, tb_max)
-        row_p70 = np.maximum(row_p70, tb_max * 0.8)
+        return p98, scale, rows[:, 0].copy(), row_p70, rows[:, 3].copy()
+
+    def upload_parametric_state(self, state):
+        """Legacy parametric rotation path (render.py:2314-2387): upload the 13 precomputed
+        component planes of a DiskTextureRotatingState (any object with its attributes) and the
+        statistics of the unrotated state; `update_disk_texture_gpu(t_offset)` then composes the
+        Kepler-rotated texture on the device."""
+        n_r, n_phi = int(state.n_r), int(state.n_phi)
+        packed = np.stack([state.temp_base, state.spiral, state.spiral_temp, state.turbulence,
+                           state.turb_temp, state.arcs, state.arcs_temp, state.rt_spikes, state.rt_temp,
+                           state.hotspot, state.hotspot_temp, state.az_hotspot, state.disturb_mod],
+                          axis=0).astype(np.float32)
+        edge, omega = _f32(state.edge), _f32(state.omega_rows)
+        self._bg_az_freq, self._bg_az_shear = 2, 2.0        # (unused: no background kernel on this path)
+        self._check(self._lib.bhr_init_background(self._ctx, n_r, n_phi, self._bg_az_freq,
+                                                  self._bg_az_shear, _fp(edge), _fp(omega)))
+        self._bg_edge_np, self._bg_omega_all_np = edge, omega
+        self._bg_n_r, self._bg_n_phi = n_r, n_phi
+        self._bg_ready = True
+        self._check(self._lib.bhr_upload_comp(self._ctx, _fp(_f32(packed))))
+        self._param_enable_rt = 1 if state.enable_rt else 0
+        self._param_color_temp = float(state.color_temp)
+        # render.py:2363-2379: raw percentiles, no floors, no base-temperature term
+        p98, scale, row_max, row_p70, _ = self._device_stats(floor_scale=False)
         self._stats = np.array([p98, scale], dtype=np.float32)
-        self._row_stats = np.column_stack([row_max, row_p70]).astype(np.float32)
+        self._row_stats = np.stack([row_max, row_p70], axis=1).astype(np.float32)
         self._push_stats()
+        self._comp_field = _Field(lambda: self._download(L.BUF_COMP, (13, n_r, n_phi), np.float32))
+        self._edge_field = _Field(lambda: self._bg_edge_np.copy())
+        self._omega_rows_field = _Field(lambda: self._bg_omega_all_np.copy())
+        self._param_stats_field = _Field(lambda: self._stats.copy())
+        self._param_row_stats_field = _Field(lambda: self._row_stats.copy())
+        self._parametric_gpu_ready = True
+
+    def update_disk_texture_gpu(self, t_offset):
+        """Compose the texture rotated by `t_offset` (each row by its Keplerian angle) and rebuild
+        the mips on the device (render.py:3792-3817)."""
+        assert getattr(self, "_parametric_gpu_ready", False), \
+            "Must call upload_parametric_state() before update_disk_texture_gpu()"
+        self._check(self._lib.bhr_compose_texture(self._ctx, float(t_offset), int(self._param_enable_rt),
+                                                  float(self._param_color_temp)))
 
     _SOLO_PAIRS = {0: [], 1: [2], 2: [1], 3: [4], 4: [3], 5: [6], 6: [5], 7: [8], 8: [7],
                    9: [10], 10: [9], 11: [], 12: []}

@@ -173,3 +173,41 @@ def test_device_statistics_equal_numpy_on_hard_inputs(case):
     s, rs = O.interactive_stats(comp, r._bg_edge_np)
     assert np.array_equal(s, r._param_stats_field.to_numpy()), (s, r._param_stats_field.to_numpy())
     assert np.array_equal(rs, r._param_row_stats_field.to_numpy())
+
+
+def test_legacy_parametric_rotation_path():
+    """upload_parametric_state + update_disk_texture_gpu (render.py:2314-2387, 3792-3817): the
+    shifted compose against the oracle for several rotation offsets, statistics = raw numpy
+    percentiles of the unrotated state."""
+    from types import SimpleNamespace
+    n_r, n_phi = 64, 256
+    rng = np.random.default_rng(3)
+    names = ["temp_base", "spiral", "spiral_temp", "turbulence", "turb_temp", "arcs", "arcs_temp",
+             "rt_spikes", "rt_temp", "hotspot", "hotspot_temp", "az_hotspot", "disturb_mod"]
+    planes = {k: rng.random((n_r, n_phi)).astype(np.float32) for k in names}
+    r_vals = 2.0 + 13.0 * np.linspace(0, 1, n_r)
+    from black_hole_renderer_b200.renderer import compute_edge_alpha
+    state = SimpleNamespace(n_r=n_r, n_phi=n_phi, enable_rt=True, color_temp=6000.0,
+                            omega_rows=np.sqrt(0.5 / (r_vals ** 3 + 1e-6)).astype(np.float32),
+                            edge=compute_edge_alpha(n_r).astype(np.float32), **planes)
+    r = _renderer(n_r, n_phi)
+    with pytest.raises(AssertionError):
+        r.update_disk_texture_gpu(0.0)
+    r.upload_parametric_state(state)
+    comp = np.stack([planes[k] for k in names])
+    density = (0.15 + 0.10 * comp[1] + 0.30 * comp[3] + 0.20 * comp[9] + 0.30 * comp[5] + 0.20 * comp[7]) * comp[12]
+    density *= state.edge[:, None]
+    ts = (comp[2] + comp[4] + comp[6] + comp[8] + comp[10]) * comp[12]
+    scale = float(np.percentile(ts[ts > 0], 95))
+    tss = np.clip(ts / (scale + 1e-6) * 0.8, 0, 1.2)
+    stats = np.array([float(np.percentile(density, 98)), scale], dtype=np.float32)
+    rows = np.stack([np.max(tss, axis=1), np.quantile(tss, 0.7, axis=1)], axis=1).astype(np.float32)
+    assert np.array_equal(stats, r._param_stats_field.to_numpy())
+    assert np.array_equal(rows, r._param_row_stats_field.to_numpy())
+    for t_offset in (0.0, 7.3, 250.0):
+        r.update_disk_texture_gpu(t_offset)
+        want = O.compose_texture(comp, state.omega_rows, state.edge, stats, rows, t_offset=t_offset)
+        got = r.disk_texture_field.to_numpy()
+        assert np.abs(got - want).max() <= 2e-5, t_offset
+        assert np.abs(r.disk_mips_field.to_numpy() - O.build_mips(got, 5, numpy_order=False)).max() <= 1e-7
+    assert not np.array_equal(got, O.compose_texture(comp, state.omega_rows, state.edge, stats, rows))
