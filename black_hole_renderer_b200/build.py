@@ -4,7 +4,7 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["api.cu", "raymarch.cu", "post.cu", "texture.cu", "stats.cu"]
+SOURCES = ["api.cu", "raymarch.cu", "post.cu", "texture.cu", "stats.cu", "peer.cu"]
 LIB = os.path.join(HERE, "libbhr.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default"]

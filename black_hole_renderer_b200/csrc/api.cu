@@ -93,6 +93,8 @@ extern "C" int bhr_create(const bhr_config* cfg, bhr_ctx** out) {
 extern "C" void bhr_destroy(bhr_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->cfg.device);
+    bhr_peer_detach(ctx);
+    if (ctx->peer_sync_own) cudaFree(ctx->peer_sync_own);
     if (ctx->own_stream) { cudaStreamSynchronize(ctx->own_stream); }
     void* ptrs[] = {ctx->sky, ctx->mips, ctx->tex_staging, ctx->bg, ctx->disk, ctx->hblur, ctx->blur, ctx->final_f32,
                     ctx->final_u8, ctx->cls, ctx->steps, ctx->d_flare_sums, ctx->retrace_queue, ctx->d_queue_count, ctx->d_wtab, ctx->d_wsum_x,

@@ -51,6 +51,9 @@ struct RayParams {
     int band_prequeued;
 };
 
+struct PeerSync;
+struct bhr_ctx;
+
 struct bhr_ctx {
     bhr_config cfg;
     int W, H;
@@ -88,6 +91,11 @@ struct bhr_ctx {
     cudaEvent_t ev[6];
     cudaEvent_t frame_ev[8];           // completion events of bhr_render_async slots
     cudaStream_t copy_stream;          // D2H of finished frames (bhr_render_async), overlaps the next frame
+    // peer-memory tiled frame (peer.cu)
+    int peer_rank, peer_world; unsigned peer_serial;
+    PeerSync* peer_sync_own; PeerSync* peer_sync[16]; PeerSync** d_peer_sync;
+    float* peer_hblur[16]; float* peer_final_f32[16]; uint8_t* peer_final_u8[16];
+    const float** d_row_src; void* d_flare_params;
     cudaEvent_t copy_done; int copy_pending;
     int ev_valid;
     float tint[3];
@@ -113,10 +121,22 @@ extern char g_bhr_create_error[512];
 
 static inline int bhr_div_up(int a, int b) { return (a + b - 1) / b; }
 
+// row-tiled frame over several GPUs through peer memory (peer.cu): what the V pass / composite need
+struct bhr_post_peer {
+    const float* const* row_src;     // device array [H]: the hblur buffer (own or a peer's) that holds each row
+    float* final_f32;                // where the finished rows go (rank 0's buffers; NULL = own)
+    uint8_t* final_u8;
+    const void* flare_params;        // device FlareParams reduced from all ranks' sums, or NULL
+    int (*before_composite)(bhr_ctx*);   // enqueue the back-pressure wait before the peer stores
+};
 // kernels / launchers implemented in the other translation units
 int bhr_launch_raymarch(bhr_ctx* ctx, const bhr_camera* cam, uint32_t flags, int row0, int row1);
 int bhr_launch_bloom_h(bhr_ctx* ctx, int row0, int row1);
 int bhr_launch_bloom_v_composite(bhr_ctx* ctx, uint32_t flags, int row0, int row1, const double* flare_sums_host);
+int bhr_launch_bloom_v_composite_ex(bhr_ctx* ctx, uint32_t flags, int row0, int row1, const double* flare_sums_host,
+                                    const bhr_post_peer* peer);
+int bhr_launch_flare_params(bhr_ctx* ctx, const double* d_parts, int world, void* d_flare_params);
+size_t bhr_flare_params_size();
 int bhr_launch_flare_sums(bhr_ctx* ctx, int row0, int row1);
 int bhr_launch_build_mips(bhr_ctx* ctx, int numpy_order);
 int bhr_setup_bloom_tables(bhr_ctx* ctx);

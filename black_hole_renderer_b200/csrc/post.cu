@@ -192,7 +192,8 @@ constexpr int V_TILE_ROWS = 8 * P_OUT;
 __global__ void __launch_bounds__(256) bloom_v_kernel(const float* __restrict__ hblur, float* __restrict__ blur,
                                                       int W, int H, int row0, int row1, int R,
                                                       const float* __restrict__ wtab, int wtab_stride,
-                                                      const float* __restrict__ wsum_y, size_t plane) {
+                                                      const float* __restrict__ wsum_y, size_t plane,
+                                                      const float* const* __restrict__ row_src) {
     extern __shared__ float vsm[];
     const int ch = blockIdx.z;
     const int nk = round_up(2 * R + P_OUT, P_OUT);
@@ -207,7 +208,15 @@ __global__ void __launch_bounds__(256) bloom_v_kernel(const float* __restrict__ 
     const float* src = hblur + ch * plane;
     for (int r = threadIdx.y; r < tile_rows; r += 8) {
         const int y = ty0 - R + r;
-        tile[r * 32 + threadIdx.x] = (col_ok && y >= 0 && y < H) ? __ldg(src + (size_t)y * W + x) : 0.0f;
+        float v = 0.0f;
+        if (col_ok && y >= 0 && y < H) {
+            // row-tiled frame over several GPUs: row y of the H-blurred layer is read from the HBM of
+            // the rank that produced it (same offset in every rank's buffer; peer loads over NVLink).
+            // Plain loads there: the read-only path must not cache another GPU's live data.
+            if (row_src) v = row_src[y][ch * plane + (size_t)y * W + x];
+            else v = __ldg(src + (size_t)y * W + x);
+        }
+        tile[r * 32 + threadIdx.x] = v;
     }
     __syncthreads();
     float acc[P_OUT], wr[P_OUT];
@@ -246,7 +255,9 @@ template <bool BLOOM, int VEC, bool FLARE>
 __global__ void __launch_bounds__(256) composite_kernel(const float* __restrict__ bg, const float* __restrict__ disk,
                                                         const float* __restrict__ blur, float* __restrict__ final_f32,
                                                         uint8_t* __restrict__ final_u8, int W, int row0, int row1,
-                                                        size_t plane, FlareParams F) {
+                                                        size_t plane, FlareParams F_arg, const FlareParams* __restrict__ F_dev) {
+    // (peer path: the flare parameters are reduced on the device from every rank's partial sums)
+    const FlareParams F = F_dev ? *F_dev : F_arg;
     const int groups_per_row = (W + VEC - 1) / VEC;
     const size_t n = (size_t)(row1 - row0) * groups_per_row;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -276,7 +287,7 @@ __global__ void __launch_bounds__(256) composite_kernel(const float* __restrict_
                 v[c][j] = fminf(fmaxf(t, 0.0f), 1.0f);
             }
         }
-        if (FLARE) {
+        if (FLARE && F.enabled) {
 #pragma unroll
             for (int j = 0; j < VEC; ++j) {
                 float fl[3];
@@ -403,7 +414,46 @@ int bhr_launch_flare_sums(bhr_ctx* ctx, int row0, int row1) {
 }
 
 // flare_sums_host: {sum B, sum x*B, sum y*B} over the WHOLE frame, or NULL for no flare
-int bhr_launch_bloom_v_composite(bhr_ctx* ctx, uint32_t flags, int row0, int row1, const double* sums) {
+namespace {
+// Device-side version of the host code below, for the peer path: total = sum of the ranks' partial
+// sums in rank order (f64), then the flare parameters of render.py:3929-3942.
+__global__ void flare_params_kernel(const double* __restrict__ parts /* [world][3] */, int world, int W, int H,
+                                    FlareParams* __restrict__ out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    for (int r = 0; r < world; ++r) { s0 += parts[3 * r]; s1 += parts[3 * r + 1]; s2 += parts[3 * r + 2]; }
+    FlareParams F;
+    F.enabled = 0; F.light_x = F.light_y = F.scx = F.scy = F.scale = F.intensity = F.streak_alpha = F.streak_len = 0.0;
+    const float total_f = (float)s0;
+    if (!(total_f < 0.01f)) {
+        F.enabled = 1;
+        F.scale = (double)(W < H ? W : H) / 360.0;
+        F.light_x = s1 / (double)total_f;
+        F.light_y = s2 / (double)total_f;
+        F.scx = W / 2.0; F.scy = H / 2.0;
+        const float qf = __fdiv_rn(total_f, (float)((double)(W * H) * 0.3));
+        if (1.0f < qf) { F.intensity = 1.0 * 1.5; F.streak_alpha = F.intensity * 0.3; }
+        else { const float it = __fmul_rn(qf, 1.5f); F.intensity = it; F.streak_alpha = __fmul_rn(it, 0.3f); }
+        F.streak_len = (double)(W < H ? W : H) * 0.4;
+    }
+    *out = F;
+}
+
+}  // namespace
+
+int bhr_launch_flare_params(bhr_ctx* ctx, const double* d_parts, int world, void* d_flare_params) {
+    flare_params_kernel<<<1, 32, 0, ctx->stream>>>(d_parts, world, ctx->W, ctx->H, (FlareParams*)d_flare_params);
+    BHR_CUDA(ctx, cudaGetLastError());
+    return BHR_OK;
+}
+size_t bhr_flare_params_size() { return sizeof(FlareParams); }
+
+// flare_sums_host: {sum B, sum x*B, sum y*B} over the WHOLE frame, or NULL for no flare.
+// peer (row-tiled frame over several GPUs, peer.cu): halo rows of the H-blurred layer come from the
+// neighbours' buffers (row_src), the flare parameters from device memory, and the finished rows are
+// written into rank 0's final buffers.
+int bhr_launch_bloom_v_composite_ex(bhr_ctx* ctx, uint32_t flags, int row0, int row1, const double* sums,
+                                    const bhr_post_peer* peer) {
     if (row1 <= row0) return BHR_OK;
     const int W = ctx->W, H = ctx->H;
     FlareParams F;
@@ -433,17 +483,25 @@ int bhr_launch_bloom_v_composite(bhr_ctx* ctx, uint32_t flags, int row0, int row
             BHR_CUDA(ctx, cudaFuncSetAttribute(bloom_v_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 block(32, 8), grid(bhr_div_up(W, 32), bhr_div_up(row1 - row0, V_TILE_ROWS), 3);
         bloom_v_kernel<<<grid, block, smem, ctx->stream>>>(ctx->hblur, ctx->blur, W, H, row0, row1, ctx->bloom_R,
-                                                          ctx->d_wtab, ctx->wtab_stride, ctx->d_wsum_y, plane);
+                                                          ctx->d_wtab, ctx->wtab_stride, ctx->d_wsum_y, plane,
+                                                          peer ? peer->row_src : nullptr);
         BHR_CUDA(ctx, cudaGetLastError());
     }
     if (ctx->copy_pending) {      // a frame is still being copied out of the final buffers (bhr_render_async)
         BHR_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copy_done, 0));
         ctx->copy_pending = 0;
     }
+    if (peer && peer->before_composite) {
+        int rc = peer->before_composite(ctx);
+        if (rc) return rc;
+    }
+    float* dst_f32 = peer && peer->final_f32 ? peer->final_f32 : ctx->final_f32;
+    uint8_t* dst_u8 = peer && peer->final_u8 ? peer->final_u8 : ctx->final_u8;
+    const FlareParams* F_dev = peer ? (const FlareParams*)peer->flare_params : nullptr;
     const int cgrid = 148 * 8;
 #define BHR_COMPOSITE(B, V, FL) composite_kernel<B, V, FL><<<cgrid, 256, 0, ctx->stream>>>( \
-        ctx->bg, ctx->disk, ctx->blur, ctx->final_f32, ctx->final_u8, W, row0, row1, plane, F)
-    const bool vec = (W % 4 == 0), fl = F.enabled != 0;
+        ctx->bg, ctx->disk, ctx->blur, dst_f32, dst_u8, W, row0, row1, plane, F, F_dev)
+    const bool vec = (W % 4 == 0), fl = F.enabled != 0 || F_dev != nullptr;
     if (vec) {
         if (bloom) { if (fl) BHR_COMPOSITE(true, 4, true); else BHR_COMPOSITE(true, 4, false); }
         else { if (fl) BHR_COMPOSITE(false, 4, true); else BHR_COMPOSITE(false, 4, false); }
@@ -454,4 +512,8 @@ int bhr_launch_bloom_v_composite(bhr_ctx* ctx, uint32_t flags, int row0, int row
 #undef BHR_COMPOSITE
     BHR_CUDA(ctx, cudaGetLastError());
     return BHR_OK;
+}
+
+int bhr_launch_bloom_v_composite(bhr_ctx* ctx, uint32_t flags, int row0, int row1, const double* sums) {
+    return bhr_launch_bloom_v_composite_ex(ctx, flags, row0, row1, sums, nullptr);
 }

@@ -148,3 +148,42 @@ def render_tiled(renderer, cam_pos, fov, frame=0, skip_differentials=False, skip
     host.copy_(frame_t, non_blocking=True)
     torch.cuda.current_stream(renderer.cuda_device).synchronize()
     return host.numpy().copy() if copy else host.numpy()     # copy=False: valid until the next call
+
+
+# ----------------------------------------------------------------------------------------------
+# The same split with peer memory instead of NCCL (csrc/peer.cu): the kernels read their halo rows
+# from the neighbours' HBM and store the finished rows into rank 0's buffers over NVLink.
+# torch.distributed is used once, to pass the CUDA IPC handles around.
+# ----------------------------------------------------------------------------------------------
+def attach_peers(renderer, rank, world_size, group=None):
+    """Exchange the IPC handles of the renderer's shared buffers between the ranks and map the
+    peers' buffers (once per renderer; every rank must call it)."""
+    import ctypes as C
+    handles = (C.c_ubyte * 256)()
+    L.check(renderer._ctx, renderer._lib.bhr_peer_export(renderer._ctx, handles))
+    everyone = [None] * world_size
+    dist.all_gather_object(everyone, bytes(handles), group=group)
+    blob = b"".join(everyone)
+    buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+    L.check(renderer._ctx, renderer._lib.bhr_peer_attach(renderer._ctx, rank, world_size, buf))
+    renderer._peer_rank, renderer._peer_world = rank, world_size
+
+
+def render_tiled_peer(renderer, cam_pos, fov, frame=0, skip_differentials=False, skip_bloom=False, out=None):
+    """One frame over all attached GPUs.  Rank 0 returns the 8-bit (H, W, 3) frame (in `out`, a
+    `renderer.pinned_frame(np.uint8)` array, allocated on first use); the others return None as
+    soon as their tile is enqueued.  No collective and no host synchronisation except rank 0's
+    final wait for the frame."""
+    import ctypes as C
+    cam = renderer._camera(cam_pos, fov, frame)
+    flags = renderer._flags(skip_differentials, skip_bloom)
+    ptr = None
+    if renderer._peer_rank == 0:
+        if out is None:
+            out = renderer.__dict__.get("_peer_out")
+            if out is None:
+                out = renderer._peer_out = renderer.pinned_frame(np.uint8)
+        assert out.dtype == np.uint8 and out.flags.c_contiguous
+        ptr = out.ctypes.data
+    L.check(renderer._ctx, renderer._lib.bhr_render_tiled_peer(renderer._ctx, C.byref(cam), flags, None, ptr))
+    return out if renderer._peer_rank == 0 else None

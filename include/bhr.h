@@ -129,6 +129,21 @@ int bhr_render_rows_stage2(bhr_ctx* ctx, uint32_t flags, int row0, int row1,
 int bhr_flare_sums(bhr_ctx* ctx, int row0, int row1, double out[3]);
 int bhr_bloom_radius(const bhr_ctx* ctx);
 
+/* ---- the same split with peer memory instead of NCCL (one process per GPU on one node) ----
+ * bhr_peer_export returns CUDA IPC handles of {H-blurred layer, final f32, final u8, sync block};
+ * the caller exchanges them between the ranks (any transport; dist.py uses all_gather_object)
+ * and hands all of them (world x 4, rank-major) to bhr_peer_attach.  bhr_render_tiled_peer then
+ * renders this rank's row tile: the vertical bloom pass loads its halo rows straight from the
+ * neighbours' HBM over NVLink, the flare sums are exchanged and reduced by kernels, the finished
+ * rows are stored straight into rank 0's final buffers, and rank 0 (the only rank whose out_*
+ * are used) copies the frame to the host.  No collective library, no host synchronisation between
+ * the stages; every rank must call it once per frame. */
+typedef struct { unsigned char bytes[64]; } bhr_ipc_handle;
+int bhr_peer_export(bhr_ctx* ctx, bhr_ipc_handle out[4]);
+int bhr_peer_attach(bhr_ctx* ctx, int rank, int world, const bhr_ipc_handle* all);
+int bhr_render_tiled_peer(bhr_ctx* ctx, const bhr_camera* cam, uint32_t flags, float* out_f32, uint8_t* out_u8);
+int bhr_peer_detach(bhr_ctx* ctx);
+
 /* ---- device buffers ---- */
 int bhr_buffer(bhr_ctx* ctx, int id, void** dev_ptr, size_t* bytes);
 int bhr_download(bhr_ctx* ctx, int id, void* host, size_t bytes);

@@ -42,5 +42,21 @@ if rank == 0:
     d = np.abs(frame.astype(int) - single.astype(int))
     print(f"4K AA+tilt+flare tiled over {world} GPU(s): {ms.item():.3f} ms/frame (u8 frame gathered to rank 0's host), "
           f"{W * H / ms.item() / 1e3:.1f} Mrays/s; vs one-GPU frame: max|d| {d.max()}, differing pixels {(d.max(-1) > 0).sum()}")
+# ---- the same frame through peer memory (csrc/peer.cu) ----
 if world > 1:
+    from black_hole_renderer_b200.dist import attach_peers, render_tiled_peer
+    attach_peers(r, rank, world)
+    for _ in range(3):
+        f2 = render_tiled_peer(r, pov, fov)
+    torch.cuda.synchronize(); dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        f2 = render_tiled_peer(r, pov, fov)
+    torch.cuda.synchronize()
+    ms = torch.tensor([(time.perf_counter() - t0) * 1e3 / K], dtype=torch.float64, device="cuda")
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        d = np.abs(f2.astype(int) - single.astype(int))
+        print(f"  peer-memory path (no NCCL on the data path): {ms.item():.3f} ms/frame, {W * H / ms.item() / 1e3:.1f} Mrays/s; "
+              f"vs one-GPU frame: max|d| {d.max()}, differing pixels {(d.max(-1) > 0).sum()}")
     dist.barrier(); dist.destroy_process_group()
