@@ -92,37 +92,45 @@ def cpu_port_frame(width, height, sky, tex, threads=None):
 
 
 def orbit_video_block(r, n_r, n_phi, rank, world, dist, torch, block=60, n_frames_total=3600):
-    """Frames/s of the orbit video path (render.py --video --orbit --n_frames 3600 -r fhd): frames
-    are dealt to ranks in 60-frame blocks (the statistics cadence); every rank replays the host
-    lifecycle ticks of all frames, and for its own block runs background + entity layer +
-    [statistics on the block's first frame] + compose + mips + ray march + bloom + composite and
-    reads the 8-bit frame back into pinned host memory.  PNG / x264 encoding is excluded."""
+    """Steady-state frames/s of the orbit video path (render.py --video --orbit --n_frames 3600
+    -r fhd).  Frames are dealt to ranks in 60-frame blocks (the statistics cadence); every rank
+    replays the host lifecycle ticks of ALL frames.  Timed: one full cycle of 60 x world frames
+    per rank, starting at the rank's own block (the ticks up to there run before the clock starts):
+    60 frames of background + entity layer + [statistics on the block's first frame] + compose +
+    mips + ray march + bloom + composite with the 8-bit frame copied to pinned host memory, then
+    the ticks of the other ranks' 60 x (world - 1) frames, which the host runs while the device
+    drains the pipeline.  PNG / x264 encoding is excluded."""
     from black_hole_renderer_b200.driver import frame_owner, orbit_camera
     from black_hole_renderer_b200.lifecycle import advance_lifecycle_frame, init_lifecycle_system
     factories = init_lifecycle_system(r, n_r, n_phi, seed=42)
-    bufs = [r.pinned_frame(np.uint8) for _ in range(2)]
+    depth = 3
+    bufs = [r.pinned_frame(np.uint8) for _ in range(depth + 1)]
     dt = 0.1
+    for frame in range(block * rank):                 # untimed: bring the lifecycle to my block
+        for f in factories.values():
+            f.tick(now=frame * dt, dt=dt)
     r.render_u8(POV, FOV, out=bufs[0])
     torch.cuda.synchronize()
     if dist:
         dist.barrier()
     t0 = time.perf_counter()
-    issued, in_flight = 0, None
-    for frame in range(block * world):
+    issued, in_flight = 0, []
+    for frame in range(block * rank, block * rank + block * world):
         t = frame * dt
         if frame_owner(frame, world, block) != rank:
             for f in factories.values():
                 f.tick(now=t, dt=dt)
             continue
-        # pipelined like driver.render_video: enqueue frame i, then wait for frame i - 1
+        # pipelined like driver.render_video: the host runs up to `depth` frames ahead
         advance_lifecycle_frame(r, factories, t, dt, recompute_stats=(frame % block == 0))
-        r.render_u8_async(orbit_camera(POV, frame, n_frames_total, 360.0), FOV, bufs[issued % 2], issued % 2)
-        if in_flight is not None:
-            r.wait_frame(in_flight)
-        in_flight = issued % 2
+        slot = issued % (depth + 1)
+        r.render_u8_async(orbit_camera(POV, frame, n_frames_total, 360.0), FOV, bufs[slot], slot)
+        in_flight.append(slot)
+        if len(in_flight) > depth:
+            r.wait_frame(in_flight.pop(0))
         issued += 1
-    if in_flight is not None:
-        r.wait_frame(in_flight)
+    for slot in in_flight:
+        r.wait_frame(slot)
     torch.cuda.synchronize()
     sec = time.perf_counter() - t0
     tt = torch.tensor([sec], dtype=torch.float64, device="cuda")
@@ -131,8 +139,9 @@ def orbit_video_block(r, n_r, n_phi, rank, world, dist, torch, block=60, n_frame
     sec = float(tt.item())
     return {"frames_per_s": block * world / sec, "frames": block * world, "seconds_max_over_ranks": sec,
             "ms_per_frame_per_gpu": 1e3 * sec / block,
-            "includes": "host lifecycle ticks of all frames on every rank, background + entity + compose + mips "
-                        "kernels, statistics on each block's first frame, render, 8-bit frame D2H to pinned memory",
+            "includes": "one steady-state cycle per rank: host lifecycle ticks of all 60 x N frames, and for the rank's own "
+                        "60 frames background + entity + compose + mips kernels, statistics on the block's first frame, "
+                        "render, 8-bit frame D2H to pinned memory",
             "excludes": "PNG / x264 encoding (host I/O)", "sharding": f"{block}-frame blocks round-robin, no collective"}
 
 

@@ -150,13 +150,15 @@ def render_video(renderer, width, height, n_frames, fps, output_path, fov, stati
         for f in range(max(completed) + 1):
             advance_lifecycle_frame(renderer, factories, f * dt, dt)
 
-    # Pipelined loop: frame i is enqueued without waiting (texture kernels, render, D2H into one of
-    # RING pinned buffers); while the device works on it the host waits for frame i - 1, hands its
-    # buffer to the PNG pool and runs the lifecycle tick / entity packing of frame i + 1.
-    RING = 8
+    # Pipelined loop: frames are enqueued without waiting (texture kernels, render, D2H into one of
+    # RING pinned buffers) and the host runs up to DEPTH frames ahead of the device: it does the
+    # lifecycle ticks / entity packing of the next frames -- and, with several ranks, the ticks of
+    # the frames other ranks own -- while the device works; a frame is retired (waited for, handed
+    # to the PNG pool) when DEPTH newer ones are in flight.
+    RING, DEPTH = 8, 3
     bufs = [renderer.pinned_frame(np.uint8) for _ in range(RING)]
     busy = [None] * RING                       # PNG job still reading the buffer
-    in_flight = None                           # (frame, slot) enqueued, not yet waited for
+    in_flight = []                             # (frame, slot) enqueued, not yet waited for
 
     def retire(item):
         frame_done, slot = item
@@ -182,17 +184,17 @@ def render_video(renderer, width, height, n_frames, fps, output_path, fov, stati
             busy[slot] = None
         advance_lifecycle_frame(renderer, factories, t, dt, recompute_stats=(frame % STATS_PERIOD == 0))
         renderer.render_u8_async(cam_pos, fov, bufs[slot], slot, frame=0)
-        if in_flight is not None:
-            retire(in_flight)
-        in_flight = (frame, slot)
+        in_flight.append((frame, slot))
+        if len(in_flight) > DEPTH:
+            retire(in_flight.pop(0))
         rendered += 1
         if rendered % 10 == 0:
             with open(my_progress, "w") as f:
                 json.dump({"params": params, "completed": sorted(completed)}, f)
         if rendered % 100 == 0:
             print(f"  [rank {rank}] frame {frame}/{n_frames}, {rendered / (time.time() - t_start):.1f} frames/s")
-    if in_flight is not None:
-        retire(in_flight)
+    for item in in_flight:
+        retire(item)
     pending = [b for b in busy if b is not None]
     for f in pending:
         f.result()

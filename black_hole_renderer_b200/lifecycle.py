@@ -227,6 +227,7 @@ class EntityFactory:
         self._spawn_debt = 0.0
         self._version = 0          # bumped whenever the population changes (SoA cache key)
         self._soa = None
+        self._cull = None          # column cache of the filament cull: [list identity, birth, s0, alpha, tau]
         self.entity_type = entity_type
         if entity_type not in _DRAW:
             raise ValueError(f"unknown entity_type {entity_type!r}")
@@ -263,20 +264,7 @@ class EntityFactory:
     def tick(self, now, dt):
         before = len(self.entities)
         if self.entity_type == "filament":
-            # inlined EntityInstance.is_dead (same arithmetic, same math.exp), 200 per frame
-            exp, thr, tmax = math.exp, FILAMENT_DEATH_THRESHOLD, FILAMENT_MAX_LIFETIME
-            keep = []
-            for e in self.entities:
-                age = now - e.birth_time
-                if age >= tmax:
-                    continue
-                if age >= 0:
-                    s0 = max(e.blob_sigma_phi0, 1e-6)
-                    cool = exp(-age / e.tau_cool) if e.tau_cool > 0 else 1.0
-                    if (s0 / (s0 + e.alpha_shear * age)) * cool < thr:
-                        continue
-                keep.append(e)
-            self.entities = keep
+            self._cull_filaments(now)
         else:
             self.entities = [e for e in self.entities
                              if now - e.birth_time < e.fade_in + e.lifetime + e.fade_out]
@@ -290,9 +278,56 @@ class EntityFactory:
         n_spawn = min(int(self._spawn_debt), deficit)
         self._spawn_debt -= n_spawn
         for _ in range(n_spawn):
-            self.entities.append(self._spawn_one(now))
+            e = self._spawn_one(now)
+            self.entities.append(e)
+            if self.entity_type == "filament":
+                self._cull_append(e)
         if n_spawn:
             self._version += 1
+
+    def _cull_filaments(self, now):
+        """EntityInstance.is_dead for every filament (render.py:560-621 semantics).  The decision
+        `shear * cool < threshold` is evaluated vectorised (numpy exp) on a column cache that is
+        kept in step with the list; the few entities within 1e-12 of the threshold -- where
+        numpy's exp and math.exp could disagree in the last ulp -- are re-decided with the scalar
+        arithmetic the reference uses, so the population (and with it the RNG call order) is
+        exactly the reference's."""
+        ents = self.entities
+        c = self._cull
+        if c is None or c[0] is not ents or len(c[1]) != len(ents):
+            n = len(ents)
+            tau = np.array([e.tau_cool for e in ents], dtype=np.float64).reshape(n)
+            c = self._cull = [ents,
+                              np.array([e.birth_time for e in ents], dtype=np.float64).reshape(n),
+                              np.array([max(e.blob_sigma_phi0, 1e-6) for e in ents], dtype=np.float64).reshape(n),
+                              np.array([e.alpha_shear for e in ents], dtype=np.float64).reshape(n),
+                              np.where(tau > 0, -1.0 / np.where(tau > 0, tau, 1.0), 0.0)]     # -1 / tau (0: no cooling)
+        if not ents:
+            return
+        _, birth, s0, alpha, neg_inv_tau = c
+        age = now - birth
+        val = s0 / (s0 + alpha * age) * np.exp(age * neg_inv_tau)
+        thr, tmax = FILAMENT_DEATH_THRESHOLD, FILAMENT_MAX_LIFETIME
+        live = age >= 0
+        dead = (age >= tmax) | (live & (val < thr))
+        close = live & (np.abs(val - thr) < 1e-12)
+        for i in (np.nonzero(close)[0] if close.any() else ()):
+            e, a = ents[i], now - ents[i].birth_time
+            if a >= tmax:
+                continue
+            cl = math.exp(-a / e.tau_cool) if e.tau_cool > 0 else 1.0
+            dead[i] = (max(e.blob_sigma_phi0, 1e-6) / (max(e.blob_sigma_phi0, 1e-6) + e.alpha_shear * a)) * cl < thr
+        if dead.any():
+            keep = ~dead
+            self.entities = [e for e, k in zip(ents, keep) if k]
+            self._cull = [self.entities, birth[keep], s0[keep], alpha[keep], neg_inv_tau[keep]]
+
+    def _cull_append(self, e):
+        c = self._cull
+        if c is not None and c[0] is self.entities and len(c[1]) == len(self.entities) - 1:
+            c[1] = np.append(c[1], e.birth_time); c[2] = np.append(c[2], max(e.blob_sigma_phi0, 1e-6))
+            c[3] = np.append(c[3], e.alpha_shear)
+            c[4] = np.append(c[4], -1.0 / e.tau_cool if e.tau_cool > 0 else 0.0)
 
     @property
     def alive_entities(self):
