@@ -248,15 +248,21 @@ class Renderer:
                                          out.ctypes.data))
         return out
 
-    def render_u8_async(self, cam_pos, fov, out, slot, frame=0, skip_differentials=False, skip_bloom=False):
-        """Enqueue a frame whose 8-bit result lands in the pinned array `out` (from
-        `pinned_frame(np.uint8)`); returns at once.  `wait_frame(slot)` blocks until it is there.
-        Video loops use it to overlap the host's lifecycle work with the device (driver.py)."""
+    def render_async(self, cam_pos, fov, out, slot, frame=0, skip_differentials=False, skip_bloom=False):
+        """Enqueue a frame whose result lands in the pinned array `out` (`pinned_frame(np.float32)`
+        or `pinned_frame(np.uint8)`: the float frame of `render` or the 8-bit frame of `render_u8`);
+        returns at once.  `wait_frame(slot)` blocks until it is there.  Video loops use it to
+        overlap the host's lifecycle work and the frame copies with the device (driver.py)."""
         cam = self._camera(cam_pos, fov, frame)
-        assert out.dtype == np.uint8 and out.flags.c_contiguous
+        assert out.dtype in (np.uint8, np.float32) and out.flags.c_contiguous
+        f32 = out.ctypes.data if out.dtype == np.float32 else None
+        u8 = out.ctypes.data if out.dtype == np.uint8 else None
         self._check(self._lib.bhr_render_async(self._ctx, C.byref(cam),
-                                               self._flags(skip_differentials, skip_bloom), None,
-                                               out.ctypes.data, int(slot)))
+                                               self._flags(skip_differentials, skip_bloom), f32, u8, int(slot)))
+
+    def render_u8_async(self, cam_pos, fov, out, slot, frame=0, skip_differentials=False, skip_bloom=False):
+        assert out.dtype == np.uint8
+        self.render_async(cam_pos, fov, out, slot, frame, skip_differentials, skip_bloom)
 
     def wait_frame(self, slot):
         self._check(self._lib.bhr_wait_frame(self._ctx, int(slot)))
