@@ -189,6 +189,7 @@ __device__ void flare_pixel(const FlareParams& F, int x, int y, float fl[3]) {
 // ---------------------------------------------------------------------------------------------
 constexpr int V_TILE_ROWS = 8 * P_OUT;
 
+template <bool PEER>
 __global__ void __launch_bounds__(256) bloom_v_kernel(const float* __restrict__ hblur, float* __restrict__ blur,
                                                       int W, int H, int row0, int row1, int R,
                                                       const float* __restrict__ wtab, int wtab_stride,
@@ -210,10 +211,10 @@ __global__ void __launch_bounds__(256) bloom_v_kernel(const float* __restrict__ 
         const int y = ty0 - R + r;
         float v = 0.0f;
         if (col_ok && y >= 0 && y < H) {
-            // row-tiled frame over several GPUs: row y of the H-blurred layer is read from the HBM of
-            // the rank that produced it (same offset in every rank's buffer; peer loads over NVLink).
-            // Plain loads there: the read-only path must not cache another GPU's live data.
-            if (row_src) v = row_src[y][ch * plane + (size_t)y * W + x];
+            // PEER (row-tiled frame over several GPUs): row y of the H-blurred layer is read from the
+            // HBM of the rank that produced it (same offset in every rank's buffer; peer loads over
+            // NVLink).  Plain loads there: the read-only path must not cache another GPU's live data.
+            if (PEER) v = row_src[y][ch * plane + (size_t)y * W + x];
             else v = __ldg(src + (size_t)y * W + x);
         }
         tile[r * 32 + threadIdx.x] = v;
@@ -479,12 +480,17 @@ int bhr_launch_bloom_v_composite_ex(bhr_ctx* ctx, uint32_t flags, int row0, int 
     if (bloom) {
         const int nk = round_up(2 * ctx->bloom_R + P_OUT, P_OUT);
         size_t smem = ((size_t)ctx->wtab_stride + (size_t)(V_TILE_ROWS - P_OUT + nk) * 32) * sizeof(float);
-        if (smem > 48 * 1024)
-            BHR_CUDA(ctx, cudaFuncSetAttribute(bloom_v_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (smem > 48 * 1024) {
+            BHR_CUDA(ctx, cudaFuncSetAttribute(bloom_v_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            BHR_CUDA(ctx, cudaFuncSetAttribute(bloom_v_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        }
         dim3 block(32, 8), grid(bhr_div_up(W, 32), bhr_div_up(row1 - row0, V_TILE_ROWS), 3);
-        bloom_v_kernel<<<grid, block, smem, ctx->stream>>>(ctx->hblur, ctx->blur, W, H, row0, row1, ctx->bloom_R,
-                                                          ctx->d_wtab, ctx->wtab_stride, ctx->d_wsum_y, plane,
-                                                          peer ? peer->row_src : nullptr);
+        if (peer && peer->row_src)
+            bloom_v_kernel<true><<<grid, block, smem, ctx->stream>>>(ctx->hblur, ctx->blur, W, H, row0, row1, ctx->bloom_R,
+                                                                    ctx->d_wtab, ctx->wtab_stride, ctx->d_wsum_y, plane, peer->row_src);
+        else
+            bloom_v_kernel<false><<<grid, block, smem, ctx->stream>>>(ctx->hblur, ctx->blur, W, H, row0, row1, ctx->bloom_R,
+                                                                     ctx->d_wtab, ctx->wtab_stride, ctx->d_wsum_y, plane, nullptr);
         BHR_CUDA(ctx, cudaGetLastError());
     }
     if (ctx->copy_pending) {      // a frame is still being copied out of the final buffers (bhr_render_async)
