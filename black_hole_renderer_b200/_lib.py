@@ -55,10 +55,13 @@ SIGNATURES = {
     "bhr_upload_skybox": (C.c_int, [_P, _FP, C.c_int, C.c_int]),
     "bhr_upload_disk_texture": (C.c_int, [_P, _FP, C.c_int, C.c_int]),
     "bhr_render": (C.c_int, [_P, C.POINTER(BhrCamera), C.c_uint32, _P, _P]),
+    "bhr_host_register": (C.c_int, [_P, C.c_size_t]),
+    "bhr_host_unregister": (C.c_int, [_P]),
     "bhr_peer_export": (C.c_int, [_P, _P]),
     "bhr_peer_attach": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "bhr_render_tiled_peer": (C.c_int, [_P, C.POINTER(BhrCamera), C.c_uint32, _P, _P]),
     "bhr_peer_detach": (C.c_int, [_P]),
+    "bhr_peer_set_distributed_egress": (C.c_int, [_P, C.c_int]),
     "bhr_render_async": (C.c_int, [_P, C.POINTER(BhrCamera), C.c_uint32, _P, _P, C.c_int]),
     "bhr_wait_frame": (C.c_int, [_P, C.c_int]),
     "bhr_render_rows_stage1": (C.c_int, [_P, C.POINTER(BhrCamera), C.c_uint32, C.c_int, C.c_int]),

@@ -318,6 +318,12 @@ extern "C" int bhr_host_alloc(size_t bytes, void** out) {
     return cudaHostAlloc(out, bytes, cudaHostAllocDefault) == cudaSuccess ? BHR_OK : BHR_ERR_NOMEM;
 }
 extern "C" int bhr_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? BHR_OK : BHR_ERR_CUDA; }
+// page-lock memory the caller owns (e.g. a POSIX shared-memory frame that several ranks copy into)
+extern "C" int bhr_host_register(void* p, size_t bytes) {
+    if (!p) return BHR_ERR_INVALID;
+    return cudaHostRegister(p, bytes, cudaHostRegisterPortable) == cudaSuccess ? BHR_OK : BHR_ERR_CUDA;
+}
+extern "C" int bhr_host_unregister(void* p) { return cudaHostUnregister(p) == cudaSuccess ? BHR_OK : BHR_ERR_CUDA; }
 
 // ---------------------------------------------------------------------------------------------
 // FP32 throughput probe (roofline denominator of the integrator)

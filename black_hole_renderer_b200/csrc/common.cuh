@@ -92,7 +92,7 @@ struct bhr_ctx {
     cudaEvent_t frame_ev[8];           // completion events of bhr_render_async slots
     cudaStream_t copy_stream;          // D2H of finished frames (bhr_render_async), overlaps the next frame
     // peer-memory tiled frame (peer.cu)
-    int peer_rank, peer_world; unsigned peer_serial;
+    int peer_rank, peer_world, peer_distributed; unsigned peer_serial;
     PeerSync* peer_sync_own; PeerSync* peer_sync[16]; PeerSync** d_peer_sync;
     float* peer_hblur[16]; float* peer_final_f32[16]; uint8_t* peer_final_u8[16];
     const float** d_row_src; void* d_flare_params;

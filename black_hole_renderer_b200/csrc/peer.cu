@@ -11,8 +11,11 @@
 //             composite: finished rows are stored straight into rank 0's final buffers
 //   publish   "my rows of frame s are in place" -> every rank
 //   rank 0    waits for all tiles, copies the frame to the host, publishes "consumed s"
+//   (distributed egress: each rank copies its own rows into a shared, page-locked host frame over
+//    its own PCIe link instead of storing them into rank 0's HBM; rank 0 only waits)
 // Back-pressure: a rank starts frame s + 1 (overwrites its H-blurred rows) only when every rank has
-// finished frame s, and stores into rank 0's final buffers only when rank 0 has consumed frame s.
+// finished frame s, and touches rank 0's final buffers / the host frame only when rank 0's caller
+// has come back for frame s + 1 (i.e. is done with frame s).
 // Flags live in the memory of the rank that waits on them, so spinning is local.
 #include "common.cuh"
 
@@ -134,8 +137,15 @@ extern "C" int bhr_render_tiled_peer(bhr_ctx* ctx, const bhr_camera* cam, uint32
     const int rank = ctx->peer_rank, world = ctx->peer_world;
     const unsigned s = ++ctx->peer_serial;
     PeerSync* mine = ctx->peer_sync_own;
+    // distributed egress: every rank copies its own rows into the (shared, page-locked) host frame
+    const bool own_egress = rank != 0 && (out_f32 || out_u8);
+    const bool host_out = out_f32 || out_u8;
     int row0, row1;
     tile_rows(ctx->H, world, rank, &row0, &row1);
+    if (rank == 0) {
+        // the caller is back for another frame: it is done with frame s - 1 (host frame / final buffers)
+        peer_publish_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_peer_sync, rank, world, nullptr, s - 1, 2);
+    }
     // every rank has finished frame s - 1 (its V pass no longer reads my H-blurred rows)
     peer_wait_kernel<<<1, 32, 0, ctx->stream>>>(mine->tile_done, world, s - 1);
     int rc = bhr_render_rows_stage1(ctx, cam, flags, row0, row1);
@@ -153,25 +163,50 @@ extern "C" int bhr_render_tiled_peer(bhr_ctx* ctx, const bhr_camera* cam, uint32
     }
     bhr_post_peer peer;
     peer.row_src = ctx->d_row_src;
-    peer.final_f32 = ctx->peer_final_f32[0]; peer.final_u8 = ctx->peer_final_u8[0];
+    peer.final_f32 = own_egress ? nullptr : ctx->peer_final_f32[0];
+    peer.final_u8 = own_egress ? nullptr : ctx->peer_final_u8[0];
     peer.flare_params = flare ? ctx->d_flare_params : nullptr;
-    peer.before_composite = wait_consumed;
+    peer.before_composite = own_egress ? nullptr : wait_consumed;
     BHR_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
     rc = bhr_launch_bloom_v_composite_ex(ctx, flags, row0, row1, nullptr, &peer);
     if (rc) return rc;
     BHR_CUDA(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
     ctx->ev_valid = 1;
+    const size_t row3 = (size_t)ctx->W * 3;
+    if (own_egress) {
+        rc = wait_consumed(ctx);                 // the host frame still holds s - 1 until rank 0's caller returns for more
+        if (rc) return rc;
+        if (out_f32) BHR_CUDA(ctx, cudaMemcpyAsync(out_f32 + row0 * row3, ctx->final_f32 + row0 * row3,
+                                                   (row1 - row0) * row3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        if (out_u8) BHR_CUDA(ctx, cudaMemcpyAsync(out_u8 + row0 * row3, ctx->final_u8 + row0 * row3, (row1 - row0) * row3,
+                                                  cudaMemcpyDeviceToHost, ctx->stream));
+    }
     peer_publish_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_peer_sync, rank, world, nullptr, s, 1);
     BHR_CUDA(ctx, cudaGetLastError());
     if (rank == 0) {
-        peer_wait_kernel<<<1, 32, 0, ctx->stream>>>(mine->tile_done, world, s);
-        const size_t n3 = (size_t)ctx->W * ctx->H * 3;
-        if (out_f32) BHR_CUDA(ctx, cudaMemcpyAsync(out_f32, ctx->final_f32, n3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-        if (out_u8) BHR_CUDA(ctx, cudaMemcpyAsync(out_u8, ctx->final_u8, n3, cudaMemcpyDeviceToHost, ctx->stream));
-        peer_publish_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_peer_sync, rank, world, nullptr, s, 2);
+        const bool distributed = host_out && ctx->peer_distributed;
+        if (distributed) {
+            // my own rows go out right away; the other ranks' rows arrive over their own links
+            if (out_f32) BHR_CUDA(ctx, cudaMemcpyAsync(out_f32 + row0 * row3, ctx->final_f32 + row0 * row3,
+                                                       (row1 - row0) * row3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+            if (out_u8) BHR_CUDA(ctx, cudaMemcpyAsync(out_u8 + row0 * row3, ctx->final_u8 + row0 * row3, (row1 - row0) * row3,
+                                                      cudaMemcpyDeviceToHost, ctx->stream));
+            peer_wait_kernel<<<1, 32, 0, ctx->stream>>>(mine->tile_done, world, s);
+        } else {
+            peer_wait_kernel<<<1, 32, 0, ctx->stream>>>(mine->tile_done, world, s);
+            const size_t n3 = (size_t)ctx->H * row3;
+            if (out_f32) BHR_CUDA(ctx, cudaMemcpyAsync(out_f32, ctx->final_f32, n3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+            if (out_u8) BHR_CUDA(ctx, cudaMemcpyAsync(out_u8, ctx->final_u8, n3, cudaMemcpyDeviceToHost, ctx->stream));
+        }
         BHR_CUDA(ctx, cudaGetLastError());
-        if (out_f32 || out_u8) BHR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (host_out) BHR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
+    return BHR_OK;
+}
+
+extern "C" int bhr_peer_set_distributed_egress(bhr_ctx* ctx, int enabled) {
+    if (!ctx) return BHR_ERR_INVALID;
+    ctx->peer_distributed = enabled ? 1 : 0;
     return BHR_OK;
 }
 

@@ -169,21 +169,54 @@ def attach_peers(renderer, rank, world_size, group=None):
     renderer._peer_rank, renderer._peer_world = rank, world_size
 
 
+def attach_shared_frame(renderer, rank, world_size, group=None, dtype=np.uint8):
+    """Distributed egress: one (H, W, 3) host frame in POSIX shared memory, mapped and page-locked
+    by every rank, so that each rank copies its own rows to the host over its own PCIe link.
+    Returns the numpy view (rank 0's result buffer).  Call once per renderer after attach_peers."""
+    from multiprocessing import shared_memory
+    nbytes = renderer.height * renderer.width * 3 * np.dtype(dtype).itemsize
+    names = [None]
+    if rank == 0:
+        shm = shared_memory.SharedMemory(create=True, size=nbytes)
+        names = [shm.name]
+    dist.broadcast_object_list(names, src=0, group=group)
+    if rank != 0:
+        shm = shared_memory.SharedMemory(name=names[0])
+    frame = np.ndarray((renderer.height, renderer.width, 3), dtype=dtype, buffer=shm.buf)
+    L.check(renderer._ctx, renderer._lib.bhr_host_register(frame.ctypes.data, nbytes))
+    L.check(renderer._ctx, renderer._lib.bhr_peer_set_distributed_egress(renderer._ctx, 1))
+    dist.barrier(group=group)
+    if rank == 0:
+        shm.unlink()                      # the mappings keep it alive; nothing is left behind in /dev/shm
+    renderer._shared_frame, renderer._shared_shm = frame, shm
+    return frame
+
+
 def render_tiled_peer(renderer, cam_pos, fov, frame=0, skip_differentials=False, skip_bloom=False, out=None):
-    """One frame over all attached GPUs.  Rank 0 returns the 8-bit (H, W, 3) frame (in `out`, a
-    `renderer.pinned_frame(np.uint8)` array, allocated on first use); the others return None as
-    soon as their tile is enqueued.  No collective and no host synchronisation except rank 0's
-    final wait for the frame."""
+    """One frame over all attached GPUs.  Rank 0 returns the (H, W, 3) frame -- 8-bit, or float32
+    if the shared frame was created with that dtype -- in `out` (a `renderer.pinned_frame(np.uint8)`
+    array, allocated on first use) or, after `attach_shared_frame`, in the shared host frame that
+    every rank fills with its own rows; the other ranks return None as soon as their tile is
+    enqueued.  No collective and no host synchronisation except rank 0's final wait."""
     import ctypes as C
     cam = renderer._camera(cam_pos, fov, frame)
     flags = renderer._flags(skip_differentials, skip_bloom)
-    ptr = None
-    if renderer._peer_rank == 0:
+    shared = renderer.__dict__.get("_shared_frame")
+    if shared is not None:
+        out = shared
+    elif renderer._peer_rank == 0:
         if out is None:
             out = renderer.__dict__.get("_peer_out")
             if out is None:
                 out = renderer._peer_out = renderer.pinned_frame(np.uint8)
-        assert out.dtype == np.uint8 and out.flags.c_contiguous
-        ptr = out.ctypes.data
-    L.check(renderer._ctx, renderer._lib.bhr_render_tiled_peer(renderer._ctx, C.byref(cam), flags, None, ptr))
+    else:
+        out = None
+    f32 = u8 = None
+    if out is not None:
+        assert out.dtype in (np.uint8, np.float32) and out.flags.c_contiguous
+        if out.dtype == np.uint8:
+            u8 = out.ctypes.data
+        else:
+            f32 = out.ctypes.data
+    L.check(renderer._ctx, renderer._lib.bhr_render_tiled_peer(renderer._ctx, C.byref(cam), flags, f32, u8))
     return out if renderer._peer_rank == 0 else None

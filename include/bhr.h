@@ -100,6 +100,9 @@ int bhr_set_option(bhr_ctx* ctx, const char* key, double value);
 /* pinned host memory so that frame read-back DMA needs no staging copy */
 int bhr_host_alloc(size_t bytes, void** out);
 int bhr_host_free(void* p);
+/* page-lock caller-owned memory, e.g. a shared-memory frame every rank copies its rows into */
+int bhr_host_register(void* p, size_t bytes);
+int bhr_host_unregister(void* p);
 
 /* texture_field.from_numpy (render.py:2232-2233): skybox (h, w, 3) f32 host */
 int bhr_upload_skybox(bhr_ctx* ctx, const float* rgb, int h, int w);
@@ -135,13 +138,17 @@ int bhr_bloom_radius(const bhr_ctx* ctx);
  * and hands all of them (world x 4, rank-major) to bhr_peer_attach.  bhr_render_tiled_peer then
  * renders this rank's row tile: the vertical bloom pass loads its halo rows straight from the
  * neighbours' HBM over NVLink, the flare sums are exchanged and reduced by kernels, the finished
- * rows are stored straight into rank 0's final buffers, and rank 0 (the only rank whose out_*
- * are used) copies the frame to the host.  No collective library, no host synchronisation between
- * the stages; every rank must call it once per frame. */
+ * rows are stored straight into rank 0's final buffers, and rank 0 copies the frame to the host.
+ * Distributed egress: when EVERY rank passes the same host buffer (shared memory mapped in all
+ * processes, page-locked with bhr_host_register) each rank copies its own rows to the host over
+ * its own PCIe link instead, and rank 0 returns when all of them have landed.
+ * No collective library, no host synchronisation between the stages; every rank must call it once
+ * per frame, all with or all (but rank 0) without host buffers. */
 typedef struct { unsigned char bytes[64]; } bhr_ipc_handle;
 int bhr_peer_export(bhr_ctx* ctx, bhr_ipc_handle out[4]);
 int bhr_peer_attach(bhr_ctx* ctx, int rank, int world, const bhr_ipc_handle* all);
 int bhr_render_tiled_peer(bhr_ctx* ctx, const bhr_camera* cam, uint32_t flags, float* out_f32, uint8_t* out_u8);
+int bhr_peer_set_distributed_egress(bhr_ctx* ctx, int enabled);   /* all ranks, before the first frame */
 int bhr_peer_detach(bhr_ctx* ctx);
 
 /* ---- device buffers ---- */

@@ -74,6 +74,17 @@ def _peer_worker(rank, world, port, out_dir):
     if rank == 0:
         np.save(os.path.join(out_dir, "single_all.npy"), np.stack([r.render_u8(c, 90) for c in cams]))
     dist.barrier()
+    # distributed egress: every rank copies its rows into one shared, page-locked host frame
+    from black_hole_renderer_b200.dist import attach_shared_frame
+    attach_shared_frame(r, rank, world)
+    shared = []
+    for c in cams + cams[::-1]:
+        f = render_tiled_peer(r, c, 90)
+        if rank == 0:
+            shared.append(f.copy())
+    if rank == 0:
+        np.save(os.path.join(out_dir, "shared_all.npy"), np.stack(shared))
+    dist.barrier()
     r.close()
     dist.destroy_process_group()
 
@@ -92,6 +103,8 @@ def test_peer_memory_tiled_frame_equals_single_gpu(tmp_path, world):
     # the flare centroid is summed per tile (f64): last-bit differences of a few pixels at most
     assert d.max() <= 1 and (d.max(axis=-1) > 0).mean() < 1e-3
     assert np.array_equal(np.load(tmp_path / "peer.npy")[0], peer[-1])
+    shared = np.load(tmp_path / "shared_all.npy")
+    assert np.array_equal(shared[:4], peer) and np.array_equal(shared[4:], peer[::-1])
 
 
 @pytest.mark.parametrize("world", [2, 4])

@@ -59,4 +59,20 @@ if world > 1:
         d = np.abs(f2.astype(int) - single.astype(int))
         print(f"  peer-memory path (no NCCL on the data path): {ms.item():.3f} ms/frame, {W * H / ms.item() / 1e3:.1f} Mrays/s; "
               f"vs one-GPU frame: max|d| {d.max()}, differing pixels {(d.max(-1) > 0).sum()}")
+    # ---- peer memory + distributed egress: every rank copies its own rows into a shared host frame ----
+    from black_hole_renderer_b200.dist import attach_shared_frame
+    attach_shared_frame(r, rank, world)
+    for _ in range(3):
+        f3 = render_tiled_peer(r, pov, fov)
+    torch.cuda.synchronize(); dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        f3 = render_tiled_peer(r, pov, fov)
+    torch.cuda.synchronize()
+    ms = torch.tensor([(time.perf_counter() - t0) * 1e3 / K], dtype=torch.float64, device="cuda")
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        d = np.abs(f3.astype(int) - single.astype(int))
+        print(f"  peer memory + distributed egress (each rank's rows over its own PCIe link): {ms.item():.3f} ms/frame, "
+              f"{W * H / ms.item() / 1e3:.1f} Mrays/s; vs one-GPU frame: max|d| {d.max()}, differing pixels {(d.max(-1) > 0).sum()}")
     dist.barrier(); dist.destroy_process_group()
