@@ -15,6 +15,7 @@ struct RayParams {
     int W, H;                   // full frame
     int row0, row1;             // rows traced by this launch
     float cp[3], cr[3], cu[3], cf[3];
+    float tl[3];                // top-left corner of the image plane
     float pw, ph;
     float r_esc, r_esc2;
     float h_base, r_in, r_out, t_offset;
