@@ -305,3 +305,26 @@ def test_async_frames_equal_synchronous_frames():
         got.append(bufs[i % 3].copy())
     assert all(np.array_equal(a, b) for a, b in zip(got, want))
     assert not np.array_equal(want[0], want[3])
+
+
+def test_physics_capture_iff_subcritical_impact_parameter():
+    """Physics known-answer test through the C-ABI: a ray ends in the horizon iff its
+    impact parameter at infinity b = L / sqrt(1 - L^2 / r_cam^3) is below 3 sqrt(3) / 2, for every
+    pixel of an sd frame outside a 0.3 % band around the critical value; shadow fraction ~ 9.7 %."""
+    r, sky, tex, pov, fov, W, H = _scene("sd")
+    r.render(pov, fov, aux=True)
+    cls, steps = r.last_aux()
+    p, right, up, fwd, pw, ph = O.build_camera(pov, fov, W, H)
+    xs = (np.arange(W) + 0.5 - W / 2) * pw
+    ys = -(np.arange(H) + 0.5 - H / 2) * ph
+    d = fwd[None, None, :] + xs[None, :, None] * right[None, None, :] + ys[:, None, None] * up[None, None, :]
+    d /= np.linalg.norm(d, axis=-1, keepdims=True)
+    L = np.linalg.norm(np.cross(d, p[None, None, :]), axis=-1)
+    b = L / np.sqrt(np.maximum(1 - L * L / np.linalg.norm(p) ** 3, 1e-9))
+    eps = b / (1.5 * np.sqrt(3.0)) - 1
+    horizon = (cls & 3) == 1
+    clear = np.abs(eps) > 3e-3
+    assert np.array_equal(horizon[clear], (eps < 0)[clear])
+    assert 0.09 < horizon.mean() < 0.105
+    # the captured rays stop early, the ones that graze the photon sphere integrate the longest
+    assert steps[horizon].mean() < steps[~horizon].mean() < steps[np.abs(eps) < 0.02].mean()
