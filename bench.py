@@ -103,7 +103,7 @@ def orbit_video_block(r, n_r, n_phi, rank, world, dist, torch, block=60, n_frame
     from black_hole_renderer_b200.driver import frame_owner, orbit_camera
     from black_hole_renderer_b200.lifecycle import advance_lifecycle_frame, init_lifecycle_system
     factories = init_lifecycle_system(r, n_r, n_phi, seed=42)
-    depth = 3
+    depth = 7                                         # frames the host may run ahead (8 completion slots)
     bufs = [r.pinned_frame(np.uint8) for _ in range(depth + 1)]
     dt = 0.1
     for frame in range(block * rank):                 # untimed: bring the lifecycle to my block

@@ -101,7 +101,7 @@ extern "C" void bhr_destroy(bhr_ctx* ctx) {
                     ctx->d_wsum_y, ctx->comp, ctx->edge, ctx->omega_rows, ctx->row_stats, ctx->d_entities, ctx->stats_scratch, ctx->stats_state, ctx->d_coltab};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int k = 0; k < 6; ++k) if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
-    for (int k = 0; k < 4; ++k) if (ctx->ent_ev[k]) cudaEventDestroy(ctx->ent_ev[k]);
+    for (int k = 0; k < 8; ++k) if (ctx->ent_ev[k]) cudaEventDestroy(ctx->ent_ev[k]);
     for (int k = 0; k < 8; ++k) if (ctx->frame_ev[k]) cudaEventDestroy(ctx->frame_ev[k]);
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
     if (ctx->copy_done) cudaEventDestroy(ctx->copy_done);

@@ -84,8 +84,8 @@ struct bhr_ctx {
     float *edge, *omega_rows, *row_stats;
     float stats[2];
     int bg_ready, az_freq; float az_shear;
-    bhr_entity* d_entities; int entities_cap;      // 4-slot ring: entities + slot maps (texture.cu)
-    void* h_entities; double* d_coltab; int ent_ring; cudaEvent_t ent_ev[4];
+    bhr_entity* d_entities; int entities_cap;      // 8-slot ring: entities + slot maps (texture.cu)
+    void* h_entities; double* d_coltab; int ent_ring; cudaEvent_t ent_ev[8];
     float* stats_scratch;              // device statistics: density / structure planes, row results (stats.cu)
     void* stats_state;
 

@@ -151,18 +151,19 @@ def render_video(renderer, width, height, n_frames, fps, output_path, fov, stati
             advance_lifecycle_frame(renderer, factories, f * dt, dt)
 
     # Pipelined loop: frames are enqueued without waiting (texture kernels, render, D2H into one of
-    # RING pinned buffers) and the host runs up to DEPTH frames ahead of the device: it does the
+    # RING pinned buffers) and the host runs up to DEPTH frames ahead of the device (enough queued work to cover
+    # the ticks of a whole block of another rank's frames): it does the
     # lifecycle ticks / entity packing of the next frames -- and, with several ranks, the ticks of
     # the frames other ranks own -- while the device works; a frame is retired (waited for, handed
     # to the PNG pool) when DEPTH newer ones are in flight.
-    RING, DEPTH = 8, 3
+    RING, DEPTH = 24, 5                        # pinned frames (in flight + being PNG-encoded), run-ahead depth
     bufs = [renderer.pinned_frame(np.uint8) for _ in range(RING)]
     busy = [None] * RING                       # PNG job still reading the buffer
     in_flight = []                             # (frame, slot) enqueued, not yet waited for
 
     def retire(item):
         frame_done, slot = item
-        renderer.wait_frame(slot)
+        renderer.wait_frame(slot % 8)          # (eight completion-event slots; DEPTH + 1 <= 8 frames in flight)
         busy[slot] = pool.submit(save_png, os.path.join(temp_dir, f"frame_{frame_done:04d}.png"), bufs[slot])
         completed.add(frame_done)
 
@@ -183,7 +184,7 @@ def render_video(renderer, width, height, n_frames, fps, output_path, fov, stati
             busy[slot].result()
             busy[slot] = None
         advance_lifecycle_frame(renderer, factories, t, dt, recompute_stats=(frame % STATS_PERIOD == 0))
-        renderer.render_u8_async(cam_pos, fov, bufs[slot], slot, frame=0)
+        renderer.render_u8_async(cam_pos, fov, bufs[slot], slot % 8, frame=0)
         in_flight.append((frame, slot))
         if len(in_flight) > DEPTH:
             retire(in_flight.pop(0))
