@@ -182,6 +182,11 @@ def attach_shared_frame(renderer, rank, world_size, group=None, dtype=np.uint8):
     dist.broadcast_object_list(names, src=0, group=group)
     if rank != 0:
         shm = shared_memory.SharedMemory(name=names[0])
+        try:        # Python < 3.13 registers attached segments with the resource tracker, which would
+            from multiprocessing import resource_tracker      # unlink them again (noisily) at exit
+            resource_tracker.unregister(shm._name, "shared_memory")
+        except Exception:
+            pass
     frame = np.ndarray((renderer.height, renderer.width, 3), dtype=dtype, buffer=shm.buf)
     L.check(renderer._ctx, renderer._lib.bhr_host_register(frame.ctypes.data, nbytes))
     L.check(renderer._ctx, renderer._lib.bhr_peer_set_distributed_egress(renderer._ctx, 1))
