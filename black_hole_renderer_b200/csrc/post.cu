@@ -111,7 +111,7 @@ __device__ __forceinline__ double np_mod(double a, double b) {   // numpy.mod fo
 // Every term is zero for most pixels; squared-distance / slope pre-tests skip the sqrt / atan2 /
 // exp of terms that cannot contribute (a skipped term adds exactly 0, as in numpy).  The streak
 // mask is a discontinuity and is decided in float64 exactly like the reference.
-__device__ void flare_pixel(const FlareParams& F, int x, int y, float fl[3]) {
+__device__ __noinline__ void flare_pixel(const FlareParams& F, int x, int y, float fl[3]) {
     const double PI = 3.14159265358979323846;
     const double GUARD = 1.0 + 1e-9;
     fl[0] = fl[1] = fl[2] = 0.0f;
