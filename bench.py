@@ -346,7 +346,8 @@ def main():
         "stage_ms": stage, "rk4_steps_per_frame": total_steps,
         "e2e": {"value": rays / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_frame": e2e_ms,
                 "h2d_bytes_per_step": 64, "d2h_bytes_per_step": W * H * 12,
-                "note": "Renderer.render(cam, fov, out=pinned (H,W,3) f32): camera struct H2D, frame D2H, host sync",
+                "note": "Renderer.render(cam, fov, out=pinned (H,W,3) f32): camera struct H2D, frame D2H, host sync; the "
+                        "frame is finished in 3 row bands (photon-ring rows first) so that a band's D2H overlaps the next band's ray march",
                 "pipelined": {"value": rays / (pipe_ms * 1e-3) / 1e6, "ms_per_frame": pipe_ms,
                               "note": "same frames and bytes through Renderer.render_async / wait_frame (two pinned "
                                       "buffers): the D2H of frame i overlaps the ray march of frame i + 1"}},

@@ -2,6 +2,8 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <vector>
+
 #include "common.cuh"
 
 char g_bhr_create_error[512] = "";
@@ -72,6 +74,9 @@ extern "C" int bhr_create(const bhr_config* cfg, bhr_ctx** out) {
     ctx->retrace_min_cross = 3;
     ctx->retrace_band = 0.02f;
     ctx->band_lo_auto = 1;
+    ctx->sync_bands = 1;
+    ctx->sync_min_bytes = 16e6;
+    ctx->strict_warps = 32;
     CREATE_CHECK(cudaMemset(ctx->bg, 0, plane * 3 * sizeof(float)));
     CREATE_CHECK(cudaMemset(ctx->disk, 0, plane * 3 * sizeof(float)));
     CREATE_CHECK(cudaMemset(ctx->hblur, 0, plane * 3 * sizeof(float)));
@@ -103,6 +108,7 @@ extern "C" void bhr_destroy(bhr_ctx* ctx) {
     for (int k = 0; k < 6; ++k) if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
     for (int k = 0; k < 8; ++k) if (ctx->ent_ev[k]) cudaEventDestroy(ctx->ent_ev[k]);
     for (int k = 0; k < 8; ++k) if (ctx->frame_ev[k]) cudaEventDestroy(ctx->frame_ev[k]);
+    for (int k = 0; k < 12; ++k) if (ctx->band_ev[k]) cudaEventDestroy(ctx->band_ev[k]);
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
     if (ctx->copy_done) cudaEventDestroy(ctx->copy_done);
     if (ctx->h_entities) cudaFreeHost(ctx->h_entities);
@@ -139,6 +145,9 @@ extern "C" int bhr_set_option(bhr_ctx* ctx, const char* key, double value) {
     if (ctx && !strcmp(key, "persistent")) { ctx->persistent = (int)value; return BHR_OK; }
     if (ctx && !strcmp(key, "band_lo_auto")) { ctx->band_lo_auto = (int)value; return BHR_OK; }
     if (ctx && !strcmp(key, "pblock_big")) { ctx->pblock_big = (int)value; return BHR_OK; }
+    if (ctx && !strcmp(key, "sync_bands")) { ctx->sync_bands = (int)value; return BHR_OK; }
+    if (ctx && !strcmp(key, "sync_min_bytes")) { ctx->sync_min_bytes = value; return BHR_OK; }
+    if (ctx && !strcmp(key, "strict_warps")) { ctx->strict_warps = (int)value; return BHR_OK; }
     if (ctx) snprintf(ctx->err, sizeof(ctx->err), "unknown option %s", key);
     return BHR_ERR_INVALID;
 }
@@ -224,12 +233,133 @@ static int render_enqueue(bhr_ctx* ctx, const bhr_camera* cam, uint32_t flags, f
     return BHR_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Synchronous frame into host memory, finished in row bands.  The D2H copy of a float fhd frame
+// (24.9 MB, 0.44 ms over PCIe 5) costs almost as much as rendering it (0.67 ms); a frame whose
+// rows are finished band by band can copy the first bands out while the later ones are still
+// being traced.  Any split reproduces the one-shot frame bit for bit (every pixel is independent
+// up to the bloom's +-R rows of the H-blurred layer, and a row is finished only when those are
+// there), so the plan below is a pure scheduling decision:
+//   * band 0 = the rows that contain the photon ring.  All ill-conditioned rays (strict
+//     integrator) live there; a launch that holds any of them lasts at least one
+//     strict batch (~0.19 ms), so they go into one launch, first, where that latency is hidden;
+//   * the rows above and below it are traced afterwards in `sync_bands` further pieces each.
+// The ring is a circle around the image centre (build_camera looks at the hole): a ray at angle
+// theta from the forward axis has L = r sin(theta) and impact parameter b = L / sqrt(1 - L^2/r^3),
+// and the band is |b / b_crit - 1| < retrace_band.
+// ---------------------------------------------------------------------------------------------
+static int plan_bands(const bhr_ctx* ctx, const bhr_camera* cam, uint32_t flags, size_t out_bytes, int bands[][2], int max_bands) {
+    const int H = ctx->H, R = (flags & BHR_SKIP_BLOOM) ? 0 : ctx->bloom_R;
+    bands[0][0] = 0; bands[0][1] = H;
+    // every extra launch costs ~50 us (tile-queue tail, band list, launch gaps): bands pay when the
+    // copy they hide is longer than that -- a float fhd frame or any 4K frame, not an 8-bit fhd one
+    if (ctx->sync_bands <= 0 || (double)out_bytes < ctx->sync_min_bytes) return 1;
+    if (ctx->cfg.lens_flare && !(flags & BHR_SKIP_FLARE)) return 1;              // the flare needs the whole disk layer first
+    const double r = sqrt((double)cam->pos[0] * cam->pos[0] + (double)cam->pos[1] * cam->pos[1] + (double)cam->pos[2] * cam->pos[2]);
+    const double b = 2.598076211353316 * (1.0 + (double)ctx->retrace_band + 2e-3);
+    const double L2 = b * b / (1.0 + b * b / (r * r * r));
+    const double s2 = L2 / (r * r);
+    if (!(r > 1.6) || !(s2 < 0.98) || !(cam->pixel_h > 0.0f)) return 1;
+    const double rho = sqrt(s2 / (1.0 - s2)) / (double)cam->pixel_h;          // ring radius in pixels
+    int ya = (int)floor(0.5 * H - 0.5 - rho) - 1, yb = (int)ceil(0.5 * H - 0.5 + rho) + 2;
+    ya = ya < 0 ? 0 : ya; yb = yb > H ? H : yb;
+    const int min_rows = R + 32;
+    if (ya < min_rows && H - yb < min_rows) return 1;                           // the ring fills the frame
+    if (ya < min_rows) ya = 0;
+    if (H - yb < min_rows) yb = H;
+    int n = 0;
+    bands[n][0] = ya; bands[n][1] = yb; ++n;
+    const int pieces = ctx->sync_bands;
+    // pieces next to the ring first: together with it they complete the rows around its edges
+    for (int side = 0; side < 2; ++side) {
+        const int lo = side == 0 ? 0 : yb, hi = side == 0 ? ya : H;
+        const int rows = hi - lo;
+        if (rows <= 0) continue;
+        int k = pieces;
+        while (k > 1 && rows / k < min_rows) --k;
+        for (int i = 0; i < k && n < max_bands; ++i) {
+            // side 0 runs from the ring upwards, side 1 from the ring downwards
+            const int a = (int)((long long)rows * i / k), c = (int)((long long)rows * (i + 1) / k);
+            if (side == 0) { bands[n][0] = hi - c; bands[n][1] = hi - a; }
+            else { bands[n][0] = lo + a; bands[n][1] = lo + c; }
+            ++n;
+        }
+    }
+    return n;
+}
+
+static int render_sync_banded(bhr_ctx* ctx, const bhr_camera* cam, uint32_t flags, float* out_f32, uint8_t* out_u8) {
+    enum { MAXB = 12 };
+    int bands[MAXB][2];
+    const size_t out_bytes = (size_t)ctx->W * ctx->H * 3 * ((out_f32 ? sizeof(float) : 0) + (out_u8 ? 1 : 0));
+    const int nb = plan_bands(ctx, cam, flags, out_bytes, bands, MAXB);
+    if (nb <= 1) {
+        int rc = render_enqueue(ctx, cam, flags, out_f32, out_u8, nullptr);
+        if (rc) return rc;
+        BHR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return BHR_OK;
+    }
+    const int H = ctx->H, R = (flags & BHR_SKIP_BLOOM) ? 0 : ctx->bloom_R;
+    if (!ctx->copy_stream) BHR_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    // rows traced / finished so far; runs[] = the row ranges finished after each band
+    std::vector<uint8_t> traced((size_t)H, 0), finished((size_t)H, 0);
+    std::vector<int> pre((size_t)H + 1, 0);               // prefix sums of traced[]
+    int runs[MAXB][4][2], n_runs[MAXB];
+    int rc = BHR_OK;
+    const size_t row_f32 = (size_t)ctx->W * 3 * sizeof(float), row_u8 = (size_t)ctx->W * 3;
+    // every band is enqueued before the first copy: a copy into pageable memory blocks the host
+    for (int k = 0; k < nb && !rc; ++k) {
+        ctx->keep_step_total = k > 0;
+        rc = bhr_render_rows_stage1(ctx, cam, flags, bands[k][0], bands[k][1]);
+        ctx->keep_step_total = 0;
+        if (rc) break;
+        for (int y = bands[k][0]; y < bands[k][1]; ++y) traced[y] = 1;
+        pre[0] = 0;
+        for (int y = 0; y < H; ++y) pre[y + 1] = pre[y] + traced[y];
+        // a row can be finished when it is not finished yet and its +-R neighbourhood is traced
+        auto ready = [&](int yy) {
+            const int a = yy - R < 0 ? 0 : yy - R, c = yy + R >= H ? H - 1 : yy + R;
+            return !finished[yy] && pre[c + 1] - pre[a] == c - a + 1;
+        };
+        n_runs[k] = 0;
+        int y = 0;
+        while (y < H && !rc) {
+            if (!ready(y)) { ++y; continue; }
+            int e = y;
+            while (e < H && ready(e)) ++e;
+            if (n_runs[k] == 4) break;                                           // (cannot happen: <= 2 runs per band)
+            rc = bhr_render_rows_stage2(ctx, flags, y, e, nullptr);
+            for (int t = y; t < e; ++t) finished[t] = 1;
+            runs[k][n_runs[k]][0] = y; runs[k][n_runs[k]][1] = e; ++n_runs[k];
+            y = e;
+        }
+        if (rc) break;
+        if (!ctx->band_ev[k]) BHR_CUDA(ctx, cudaEventCreateWithFlags(&ctx->band_ev[k], cudaEventDisableTiming));
+        BHR_CUDA(ctx, cudaEventRecord(ctx->band_ev[k], ctx->stream));
+    }
+    int all = 1;
+    for (int y = 0; y < H; ++y) all &= finished[y];
+    if (rc) return rc;
+    if (!all) BHR_FAIL(ctx, BHR_ERR_STATE, "band plan left rows unfinished");
+    for (int k = 0; k < nb; ++k) {
+        BHR_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->band_ev[k], 0));
+        for (int i = 0; i < n_runs[k]; ++i) {
+            const size_t y0 = (size_t)runs[k][i][0], rows = (size_t)(runs[k][i][1] - runs[k][i][0]);
+            if (out_f32) BHR_CUDA(ctx, cudaMemcpyAsync((char*)out_f32 + y0 * row_f32, (const char*)ctx->final_f32 + y0 * row_f32,
+                                                       rows * row_f32, cudaMemcpyDeviceToHost, ctx->copy_stream));
+            if (out_u8) BHR_CUDA(ctx, cudaMemcpyAsync(out_u8 + y0 * row_u8, ctx->final_u8 + y0 * row_u8, rows * row_u8,
+                                                      cudaMemcpyDeviceToHost, ctx->copy_stream));
+        }
+    }
+    BHR_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    BHR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return BHR_OK;
+}
+
 extern "C" int bhr_render(bhr_ctx* ctx, const bhr_camera* cam, uint32_t flags, float* out_f32, uint8_t* out_u8) {
     if (!ctx || !cam) return BHR_ERR_INVALID;
-    int rc = render_enqueue(ctx, cam, flags, out_f32, out_u8, nullptr);
-    if (rc) return rc;
-    if (out_f32 || out_u8) BHR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return BHR_OK;
+    if (out_f32 || out_u8) return render_sync_banded(ctx, cam, flags, out_f32, out_u8);
+    return render_enqueue(ctx, cam, flags, nullptr, nullptr, nullptr);
 }
 
 extern "C" int bhr_render_async(bhr_ctx* ctx, const bhr_camera* cam, uint32_t flags, float* out_f32, uint8_t* out_u8, int slot) {

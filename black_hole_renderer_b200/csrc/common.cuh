@@ -50,6 +50,7 @@ struct RayParams {
     unsigned int* band_head;    // batches of 32 band rays claimed so far
     unsigned int* tile_counter; // fast tiles claimed so far
     int band_prequeued;
+    int strict_warps;           // warps per strict block that trace band batches (the rest wait, then join the fast pool)
 };
 
 struct PeerSync;
@@ -98,6 +99,10 @@ struct bhr_ctx {
     float* peer_hblur[16]; float* peer_final_f32[16]; uint8_t* peer_final_u8[16];
     const float** d_row_src; void* d_flare_params;
     cudaEvent_t copy_done; int copy_pending;
+    // synchronous frames finished in row bands (api.cu): pieces per side of the photon-ring band (0 = off),
+    // completion event per band, and "this launch continues a frame: keep the RK4 step total"
+    int sync_bands; double sync_min_bytes; cudaEvent_t band_ev[12]; int keep_step_total;
+    int strict_warps;
     int ev_valid;
     float tint[3];
 };

@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 from . import _lib as L
-from .camera import build_camera
+from .camera import build_camera, build_camera_scalar
 
 R_DISK_INNER_DEFAULT = 2.0
 R_DISK_OUTER_DEFAULT = 15.0
@@ -203,16 +203,14 @@ class Renderer:
 
     # ------------------------------------------------------------------ hot path
     def _camera(self, cam_pos, fov, frame):
-        pos, right, up, forward, pw, ph = build_camera(
-            np.array(cam_pos, dtype=np.float64), fov, self.width, self.height)
-        r_escape = max(self.r_max, float(np.linalg.norm(pos)) * 2)
+        # (scalar float64 twin of build_camera: this runs on the latency path of every frame)
+        pos, right, up, forward, pw, ph, norm = build_camera_scalar(cam_pos, fov, self.width, self.height)
         cam = L.BhrCamera()
-        for k in range(3):
-            cam.pos[k] = np.float32(pos[k])
-            cam.right[k] = np.float32(right[k])
-            cam.up[k] = np.float32(up[k])
-            cam.forward[k] = np.float32(forward[k])
-        cam.pixel_w, cam.pixel_h, cam.r_escape = float(pw), float(ph), float(r_escape)
+        cam.pos[:] = pos            # ctypes rounds float64 -> float32 to nearest, like np.float32()
+        cam.right[:] = right
+        cam.up[:] = up
+        cam.forward[:] = forward
+        cam.pixel_w, cam.pixel_h, cam.r_escape = pw, ph, max(self.r_max, norm * 2)
         cam.t_offset = float(frame) * self.disk_rotation_speed
         return cam
 

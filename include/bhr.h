@@ -95,7 +95,10 @@ int bhr_version(void);
  * >= n disk-plane crossings are re-traced too (default 3, 0 = off); "band_lo_auto" = 1 (default): with the
  * disk's inner edge outside the photon sphere the band is (-0.005, eps) -- rays safely below the
  * critical impact parameter end in the horizon whatever they do near it; "persistent" = 1 (default):
- * one block per SM with work queues, strict and fast rays on disjoint SMs; "pblock_big" */
+ * one block per SM with work queues, strict and fast rays on disjoint SMs; "pblock_big";
+ * "strict_warps" = n: warps per strict block that trace photon-ring batches (default: all; fewer
+ * spreads them over more SMs -- lower latency of a small ring tile, idle warps meanwhile);
+ * "sync_bands" / "sync_min_bytes": row bands of synchronous host frames, see bhr_render */
 int bhr_set_option(bhr_ctx* ctx, const char* key, double value);
 /* pinned host memory so that frame read-back DMA needs no staging copy */
 int bhr_host_alloc(size_t bytes, void** out);
@@ -113,7 +116,11 @@ int bhr_upload_disk_texture(bhr_ctx* ctx, const float* rgba, int n_r, int n_phi)
 
 /* ---- hot path (TaichiRenderer.render, render.py:3865-3923) ---- */
 /* Ray march + bloom + composite [+ flare]; if out_f32 / out_u8 are non-NULL the (H, W, 3)
- * result is copied to those HOST buffers (the call then synchronises). */
+ * result is copied to those HOST buffers (the call then synchronises).  Large host frames
+ * (>= option "sync_min_bytes", 16 MB) without flare are finished in row bands -- the rows of the
+ * photon ring first, then "sync_bands" pieces above and below -- so that the copy of one band
+ * overlaps the ray march of the next; the result is bit-identical to the one-shot frame, and
+ * bhr_last_stage_ms then describes the last band. */
 int bhr_render(bhr_ctx* ctx, const bhr_camera* cam, uint32_t flags, float* out_f32, uint8_t* out_u8);
 /* The same without the final synchronisation, for pipelined video loops: the frame is enqueued
  * (ray march ... composite, copies into the PINNED host buffers) and completion event `slot`

@@ -19,6 +19,31 @@ def test_build_camera():
         assert np.array_equal(flat, row[6:])
 
 
+def test_scalar_camera_uploads_the_same_float32_values():
+    """Renderer._camera forms the per-frame camera with build_camera_scalar (no numpy calls on the
+    frame's latency path); what reaches the device -- the float32 casts of render.py:3880-3892 --
+    is bit-identical to build_camera's on the reference's golden cameras, the 3600 orbit cameras,
+    random cameras and the on-axis fallback."""
+    from black_hole_renderer_b200 import build_camera
+    from black_hole_renderer_b200.camera import build_camera_scalar
+    from black_hole_renderer_b200.driver import orbit_camera
+    h = np.load(os.path.join(GOLDEN, "host.npz"))
+    cases = [(list(row[0:3]), float(row[3]), int(row[4]), int(row[5])) for row in h["cameras"]]
+    cases += [(orbit_camera([6.0, 0.0, 0.5], f, 3600, 360.0), 90.0, 1920, 1080) for f in range(0, 3600, 7)]
+    cases += [([0, 0, 8], 60.0, 160, 90), ([0, 0, -3], 45.0, 640, 360), ([1e-9, 0, 5], 90.0, 640, 360)]
+    rng = np.random.default_rng(7)
+    for _ in range(3000):
+        cases.append((list(rng.normal(size=3) * rng.uniform(0.5, 20)), float(rng.uniform(10, 150)), 1283, 727))
+    bits = lambda v: np.asarray(v, dtype=np.float64).astype(np.float32).view(np.uint32)
+    for pov, fov, w, hh in cases:
+        a = build_camera(np.array(pov, dtype=np.float64), fov, w, hh)
+        b = build_camera_scalar(pov, fov, w, hh)
+        for k in range(4):
+            assert np.array_equal(bits(a[k]), bits(b[k])), (pov, fov, k)
+        assert np.float32(a[4]) == np.float32(b[4]) and np.float32(a[5]) == np.float32(b[5])
+        assert np.float32(max(10.0, float(np.linalg.norm(a[0])) * 2)) == np.float32(max(10.0, b[6] * 2))
+
+
 def test_disk_texture_resolution():
     from black_hole_renderer_b200.driver import compute_disk_texture_resolution
     h = np.load(os.path.join(GOLDEN, "host.npz"))

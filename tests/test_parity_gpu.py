@@ -307,6 +307,48 @@ def test_async_frames_equal_synchronous_frames():
     assert not np.array_equal(want[0], want[3])
 
 
+@pytest.mark.parametrize("case", ["fhd_default", "hd_tilt_aa", "near_camera", "odd_size_skip_bloom"])
+def test_banded_synchronous_frame_equals_the_one_shot_frame(case):
+    """bhr_render into host memory finishes the frame in row bands (photon-ring rows first) so that
+    the D2H copy of one band overlaps the ray march of the next (api.cu: render_sync_banded).  The
+    split is a scheduling decision only: float and 8-bit frames, the class / step maps and the RK4
+    step total are bit-identical to the one-shot frame for every band count, pinned and pageable
+    destinations, ring bands that touch the frame edge, and odd sizes."""
+    kw, size, pov, fov, skip_bloom = {}, "fhd", [6, 0, 0.5], 90, False
+    if case == "hd_tilt_aa":
+        kw, size = dict(anti_alias="lod_radius", disk_tilt=20.0), "hd"
+    elif case == "near_camera":                       # the ring band reaches the top and bottom of the frame
+        size, pov, fov = (1280, 720), [3.0, 0.5, 0.2], 90
+    elif case == "odd_size_skip_bloom":
+        size, pov, fov, skip_bloom = (1283, 727), [5, 2, 1], 70, True
+    r, sky, tex, _, _, W, H = _scene(size, pov=pov, fov=fov, **kw)
+    r.set_option("sync_min_bytes", 0)                  # band whatever the frame size
+    r.set_option("sync_bands", 0)
+    want = r.render(pov, fov, aux=True, skip_bloom=skip_bloom).copy()
+    cls0, steps0 = r.last_aux()
+    total0 = r.last_total_steps()
+    want_u8 = r.render_u8(pov, fov, skip_bloom=skip_bloom).copy()
+    pinned = r.pinned_frame(np.float32)
+    for bands in (1, 2, 5):
+        r.set_option("sync_bands", bands)
+        got = r.render(pov, fov, aux=True, skip_bloom=skip_bloom)            # pageable destination
+        assert np.array_equal(got, want), (case, bands)
+        cls, steps = r.last_aux()
+        assert np.array_equal(cls, cls0) and np.array_equal(steps, steps0)
+        assert r.last_total_steps() == total0 == int(steps.sum())
+        r.render(pov, fov, out=pinned, skip_bloom=skip_bloom)
+        assert np.array_equal(pinned, want)
+        assert np.array_equal(r.render_u8(pov, fov, skip_bloom=skip_bloom), want_u8)
+    # frames rendered back to back into the same buffer do not race with the previous copy
+    from black_hole_renderer_b200.driver import orbit_camera
+    cams = [orbit_camera(pov, f, 36, 360.0) for f in range(3)]
+    r.set_option("sync_bands", 0)
+    refs = [r.render(c, fov, skip_bloom=skip_bloom).copy() for c in cams]
+    r.set_option("sync_bands", 1)
+    for c, ref in zip(cams, refs):
+        assert np.array_equal(r.render(c, fov, out=pinned, skip_bloom=skip_bloom), ref)
+
+
 def test_physics_capture_iff_subcritical_impact_parameter():
     """Physics known-answer test through the C-ABI: a ray ends in the horizon iff its
     impact parameter at infinity b = L / sqrt(1 - L^2 / r_cam^3) is below 3 sqrt(3) / 2, for every
