@@ -77,6 +77,7 @@ extern "C" int bhr_create(const bhr_config* cfg, bhr_ctx** out) {
     ctx->sync_bands = 1;
     ctx->sync_min_bytes = 16e6;
     ctx->strict_warps = 32;
+    ctx->band_box = 1;
     CREATE_CHECK(cudaMemset(ctx->bg, 0, plane * 3 * sizeof(float)));
     CREATE_CHECK(cudaMemset(ctx->disk, 0, plane * 3 * sizeof(float)));
     CREATE_CHECK(cudaMemset(ctx->hblur, 0, plane * 3 * sizeof(float)));
@@ -147,6 +148,7 @@ extern "C" int bhr_set_option(bhr_ctx* ctx, const char* key, double value) {
     if (ctx && !strcmp(key, "pblock_big")) { ctx->pblock_big = (int)value; return BHR_OK; }
     if (ctx && !strcmp(key, "sync_bands")) { ctx->sync_bands = (int)value; return BHR_OK; }
     if (ctx && !strcmp(key, "sync_min_bytes")) { ctx->sync_min_bytes = value; return BHR_OK; }
+    if (ctx && !strcmp(key, "band_box")) { ctx->band_box = (int)value; return BHR_OK; }
     if (ctx && !strcmp(key, "strict_warps")) { ctx->strict_warps = (int)value; return BHR_OK; }
     if (ctx) snprintf(ctx->err, sizeof(ctx->err), "unknown option %s", key);
     return BHR_ERR_INVALID;

@@ -50,6 +50,7 @@ struct RayParams {
     unsigned int* band_head;    // batches of 32 band rays claimed so far
     unsigned int* tile_counter; // fast tiles claimed so far
     int band_prequeued;
+    int band_x0, band_x1, band_y0, band_y1;   // pixels band_list_kernel scans (the ring's bounding box)
     int strict_warps;           // warps per strict block that trace band batches (the rest wait, then join the fast pool)
 };
 
@@ -102,7 +103,7 @@ struct bhr_ctx {
     // synchronous frames finished in row bands (api.cu): pieces per side of the photon-ring band (0 = off),
     // completion event per band, and "this launch continues a frame: keep the RK4 step total"
     int sync_bands; double sync_min_bytes; cudaEvent_t band_ev[12]; int keep_step_total;
-    int strict_warps;
+    int strict_warps, band_box;
     int ev_valid;
     float tint[3];
 };

@@ -98,6 +98,7 @@ int bhr_version(void);
  * one block per SM with work queues, strict and fast rays on disjoint SMs; "pblock_big";
  * "strict_warps" = n: warps per strict block that trace photon-ring batches (default: all; fewer
  * spreads them over more SMs -- lower latency of a small ring tile, idle warps meanwhile);
+ * "band_box" = 1 (default): the band-list kernel scans only the photon ring's bounding box;
  * "sync_bands" / "sync_min_bytes": row bands of synchronous host frames, see bhr_render */
 int bhr_set_option(bhr_ctx* ctx, const char* key, double value);
 /* pinned host memory so that frame read-back DMA needs no staging copy */

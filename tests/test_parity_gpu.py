@@ -349,6 +349,24 @@ def test_banded_synchronous_frame_equals_the_one_shot_frame(case):
         assert np.array_equal(r.render(c, fov, out=pinned, skip_bloom=skip_bloom), ref)
 
 
+@pytest.mark.parametrize("pov,fov,size,kw", [
+    ([6, 0, 0.5], 90, "hd", {}), ([0, 0, 8], 60, (640, 360), {}), ([4, 3, 2], 75, (333, 187), dict(disk_tilt=-35.0)),
+    ([2.5, 0, 0.3], 100, "sd", {}), ([20, 0, 3], 40, "sd", {}), ([40, 5, 3], 10, "sd", {})])
+def test_band_list_bounding_box_finds_every_band_pixel(pov, fov, size, kw):
+    """The band-list kernel scans the photon ring's bounding box only.  A band pixel it missed would
+    be traced by the fast integrator instead of the strict one, so frames, class and step maps must
+    be bit-identical with the box on and off (ring inside, across and outside the frame; on-axis camera)."""
+    r, sky, tex, _, _, W, H = _scene(size, pov=pov, fov=fov, **kw)
+    out = {}
+    for box in (0, 1):
+        r.set_option("band_box", box)
+        img = r.render(pov, fov, aux=True).copy()
+        out[box] = (img,) + r.last_aux() + (r.last_total_steps(),)
+    assert np.array_equal(out[0][0], out[1][0])
+    assert np.array_equal(out[0][1], out[1][1]) and np.array_equal(out[0][2], out[1][2])
+    assert out[0][3] == out[1][3]
+
+
 def test_physics_capture_iff_subcritical_impact_parameter():
     """Physics known-answer test through the C-ABI: a ray ends in the horizon iff its
     impact parameter at infinity b = L / sqrt(1 - L^2 / r_cam^3) is below 3 sqrt(3) / 2, for every
