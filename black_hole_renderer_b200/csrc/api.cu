@@ -148,6 +148,7 @@ extern "C" int bhr_set_option(bhr_ctx* ctx, const char* key, double value) {
     if (ctx && !strcmp(key, "pblock_big")) { ctx->pblock_big = (int)value; return BHR_OK; }
     if (ctx && !strcmp(key, "sync_bands")) { ctx->sync_bands = (int)value; return BHR_OK; }
     if (ctx && !strcmp(key, "sync_min_bytes")) { ctx->sync_min_bytes = value; return BHR_OK; }
+    if (ctx && !strcmp(key, "planar")) { ctx->planar = (int)value; return BHR_OK; }
     if (ctx && !strcmp(key, "band_box")) { ctx->band_box = (int)value; return BHR_OK; }
     if (ctx && !strcmp(key, "strict_warps")) { ctx->strict_warps = (int)value; return BHR_OK; }
     if (ctx) snprintf(ctx->err, sizeof(ctx->err), "unknown option %s", key);
@@ -312,7 +313,12 @@ static int render_sync_banded(bhr_ctx* ctx, const bhr_camera* cam, uint32_t flag
     // every band is enqueued before the first copy: a copy into pageable memory blocks the host
     for (int k = 0; k < nb && !rc; ++k) {
         ctx->keep_step_total = k > 0;
+        // the ring band alone is bounded by the latency of its strict batches: spread them over more
+        // SMs (20 instead of 28 strict warps per block: 321 -> 299 us for the fhd ring band)
+        const int strict_warps = ctx->strict_warps;
+        if (k == 0 && strict_warps > 20) ctx->strict_warps = 20;
         rc = bhr_render_rows_stage1(ctx, cam, flags, bands[k][0], bands[k][1]);
+        ctx->strict_warps = strict_warps;
         ctx->keep_step_total = 0;
         if (rc) break;
         for (int y = bands[k][0]; y < bands[k][1]; ++y) traced[y] = 1;
