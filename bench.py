@@ -56,7 +56,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except Exception:
@@ -145,6 +145,39 @@ def orbit_video_block(r, n_r, n_phi, rank, world, dist, torch, block=60, n_frame
             "excludes": "PNG / x264 encoding (host I/O)", "sharding": f"{block}-frame blocks round-robin, no collective"}
 
 
+def other_configs(Renderer, sky, peak, stream, frames=5):
+    """configs[2] (4K, ray differentials + mip LOD, tilt 20, flare) and configs[3] (fhd, step 0.02,
+    r_max 30): best-of-`frames` device time of one frame with the result left in HBM, the ray
+    march's share of it and its fraction of the measured FP32 peak (SURVEY.md 8d flop counts)."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from util import synthetic_disk_texture
+    from black_hole_renderer_b200.driver import compute_disk_texture_resolution
+    out = {}
+    cases = {"configs[2] 4k anti_alias=lod_radius disk_tilt=20 lens_flare": ("4k", dict(anti_alias="lod_radius", disk_tilt=20.0, lens_flare=True), FLOP_PER_STEP_DIFF),
+             "configs[3] fhd step_size=0.02 r_max=30": ("fhd", dict(step_size=0.02, r_max=30.0), FLOP_PER_STEP)}
+    for name, (res, kw, flop) in cases.items():
+        W, H = RES[res]
+        n_phi, n_r = compute_disk_texture_resolution(W, H, POV, FOV, 2.0, 15.0)
+        r = Renderer(W, H, sky, synthetic_disk_texture(n_r, n_phi), cuda_device=torch.cuda.current_device(), **kw)
+        r.set_stream(stream.cuda_stream)
+        best = None
+        for i in range(frames + 2):
+            r.render_device(POV, FOV)
+            r.synchronize()
+            ms = r.last_stage_ms()
+            if i >= 2 and (best is None or ms["total"] < best["total"]):
+                best = ms
+        steps = r.last_total_steps()
+        tf = flop * steps / (best["ray_march"] * 1e-3) / 1e12
+        out[name] = {"ms_per_frame": best["total"], "Mrays_per_s": W * H / (best["total"] * 1e-3) / 1e6,
+                     "stage_ms": {k: best[k] for k in ("ray_march", "bloom_h", "bloom_v_composite", "gap")},
+                     "rk4_steps_per_frame": steps, "ray_march_tflops": tf, "frac_of_fp32_peak": (tf / peak) if peak else None,
+                     "flop_per_step": flop, "disk_texture": "synthetic (texel values do not affect the timing)"}
+        r.close()
+    return out
+
+
 def profiled_traffic():
     """DRAM bytes per launch of the dominant kernel from the newest committed `ncu --set full`
     capture (profiles/*_raymarch_ncu.txt: dram__bytes_read.sum + dram__bytes_write.sum)."""
@@ -205,6 +238,7 @@ def main():
     ap.add_argument("--resolution", default="fhd", choices=list(RES))
     ap.add_argument("--mode", default=None, help="raymarch mode override: fast | strict")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -276,7 +310,6 @@ def main():
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    clocks = sampler.stop() if sampler else None
     ms_step = sum(a.elapsed_time(b) for a, b in evs) / args.steps
     t = torch.tensor([ms_step], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -319,6 +352,13 @@ def main():
 
     # ---- orbit video (BASELINE.json configs[4]): one 60-frame block per rank, whole per-frame path ----
     orbit = orbit_video_block(r, n_r, n_phi, rank, world, dist if world > 1 else None, torch)
+    clocks = sampler.stop() if sampler else None      # sampled every 20 ms over all the timed regions above
+
+    # ---- the other BASELINE.json configurations, device-resident, rank 0 at N = 1 (parity-tested in
+    #      tests/; timed here so that every config has a number next to its roofline) ----
+    other = None
+    if world == 1 and not args.no_other_configs:
+        other = other_configs(Renderer, sky, peak, stream)
 
     if rank != 0:
         if world > 1:
@@ -362,6 +402,8 @@ def main():
         "clocks": clocks,
         "orbit_video": orbit,
     }
+    if other:
+        line["other_configs"] = other
     if not args.no_cpu_baseline and world == 1:      # CPU baseline: rank 0 at N = 1 only
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         tex = r.disk_texture_field.to_numpy()
