@@ -76,6 +76,7 @@ extern "C" int bhr_create(const bhr_config* cfg, bhr_ctx** out) {
     ctx->band_lo_auto = 1;
     ctx->sync_bands = 1;
     ctx->sync_min_bytes = 16e6;
+    ctx->sync_extend = 0.1;
     ctx->strict_warps = 32;
     ctx->band_box = 1;
     CREATE_CHECK(cudaMemset(ctx->bg, 0, plane * 3 * sizeof(float)));
@@ -147,6 +148,7 @@ extern "C" int bhr_set_option(bhr_ctx* ctx, const char* key, double value) {
     if (ctx && !strcmp(key, "band_lo_auto")) { ctx->band_lo_auto = (int)value; return BHR_OK; }
     if (ctx && !strcmp(key, "pblock_big")) { ctx->pblock_big = (int)value; return BHR_OK; }
     if (ctx && !strcmp(key, "sync_bands")) { ctx->sync_bands = (int)value; return BHR_OK; }
+    if (ctx && !strcmp(key, "sync_extend")) { ctx->sync_extend = value; return BHR_OK; }
     if (ctx && !strcmp(key, "sync_min_bytes")) { ctx->sync_min_bytes = value; return BHR_OK; }
     if (ctx && !strcmp(key, "planar")) { ctx->planar = (int)value; return BHR_OK; }
     if (ctx && !strcmp(key, "band_box")) { ctx->band_box = (int)value; return BHR_OK; }
@@ -265,6 +267,9 @@ static int plan_bands(const bhr_ctx* ctx, const bhr_camera* cam, uint32_t flags,
     if (!(r > 1.6) || !(s2 < 0.98) || !(cam->pixel_h > 0.0f)) return 1;
     const double rho = sqrt(s2 / (1.0 - s2)) / (double)cam->pixel_h;          // ring radius in pixels
     int ya = (int)floor(0.5 * H - 0.5 - rho) - 1, yb = (int)ceil(0.5 * H - 0.5 + rho) + 2;
+    // the ring band is bounded by the latency of its strict batches, not by its fast rays: rows
+    // added below it are traced for free and shorten the last band (the one whose copy nothing hides)
+    yb += (int)((yb - ya) * ctx->sync_extend);
     ya = ya < 0 ? 0 : ya; yb = yb > H ? H : yb;
     const int min_rows = R + 32;
     if (ya < min_rows && H - yb < min_rows) return 1;                           // the ring fills the frame

@@ -102,7 +102,7 @@ struct bhr_ctx {
     cudaEvent_t copy_done; int copy_pending;
     // synchronous frames finished in row bands (api.cu): pieces per side of the photon-ring band (0 = off),
     // completion event per band, and "this launch continues a frame: keep the RK4 step total"
-    int sync_bands; double sync_min_bytes; cudaEvent_t band_ev[12]; int keep_step_total;
+    int sync_bands; double sync_min_bytes, sync_extend; cudaEvent_t band_ev[12]; int keep_step_total;
     int strict_warps, band_box, planar;
     int ev_valid;
     float tint[3];

@@ -54,7 +54,7 @@ def launches(csv_in, md_out, bench_log):
     tot = sum(sum(agg[k]) / len(agg[k]) for k in frame if k in agg)
     with open(os.path.join(P, md_out), "w") as f:
         f.write(f"# {TAG} launch list summary (profiles/{csv_in})\n\n")
-        f.write("Command: `ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline`\n"
+        f.write("Command: `ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-other-configs`\n"
                 f"(after the same command exited 0 without ncu: ms_per_step {bench['ms_per_step']:.4f}, stage_ms {bench['stage_ms']}).\n"
                 "Per-launch times under ncu are cold-cache and serialised: compare SHARES with bench.py's stage_ms, not absolutes.\n\n")
         f.write("| kernel | launches | mean us | share of one frame |\n|---|---|---|---|\n")
