@@ -50,20 +50,21 @@ def launches(csv_in, md_out, bench_log):
         v = v / 1000 if r[iu] == 'ns' else v * 1000 if r[iu] == 'ms' else v
         agg.setdefault(r[ik].split('(')[0].replace('void ', '').replace('<unnamed>::', ''), []).append(v)
     bench = json.loads(open(os.path.join(G, bench_log)).read().strip().splitlines()[-1])
-    frame = ['band_list_kernel', 'raymarch_persistent<0, 896>', 'retrace_kernel<0>', 'bloom_h_kernel', 'bloom_v_kernel<0>', 'composite_kernel<1, 4, 0>']
-    tot = sum(sum(agg[k]) / len(agg[k]) for k in frame if k in agg)
+    frame = ['band_list_kernel', 'raymarch_persistent<0, 896, 0>', 'retrace_kernel<0>', 'bloom_h_kernel', 'bloom_v_kernel<0>', 'composite_kernel<1, 4, 0>']
+    med = lambda v: sorted(v)[len(v) // 2]      # (median: the banded synchronous frames of the e2e block launch the same kernels on row bands)
+    tot = sum(med(agg[k]) for k in frame if k in agg)
     with open(os.path.join(P, md_out), "w") as f:
         f.write(f"# {TAG} launch list summary (profiles/{csv_in})\n\n")
         f.write("Command: `ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-other-configs`\n"
                 f"(after the same command exited 0 without ncu: ms_per_step {bench['ms_per_step']:.4f}, stage_ms {bench['stage_ms']}).\n"
                 "Per-launch times under ncu are cold-cache and serialised: compare SHARES with bench.py's stage_ms, not absolutes.\n\n")
-        f.write("| kernel | launches | mean us | share of one frame |\n|---|---|---|---|\n")
+        f.write("| kernel | launches | median us | share of one frame |\n|---|---|---|---|\n")
         for k, v in agg.items():
-            m = sum(v) / len(v)
+            m = med(v)
             share = f"{100 * m / tot:.1f} %" if k in frame else "(outside the timed frame: setup / orbit-video block / peak probe)"
             f.write(f"| {k} | {len(v)} | {m:.1f} | {share} |\n")
         st = bench['stage_ms']; s = sum(st.values())
-        rm = sum(sum(agg[k]) / len(agg[k]) for k in frame[:3] if k in agg)
+        rm = sum(med(agg[k]) for k in frame[:3] if k in agg)
         f.write(f"\nOne frame under ncu = {tot:.1f} us; ray march (band list + persistent + retrace) = {100 * rm / tot:.1f} % of it; "
                 f"bench.py stage_ms (CUDA events, no profiler): ray march {100 * st['ray_march'] / s:.1f} %, bloom H {100 * st['bloom_h'] / s:.1f} %, "
                 f"bloom V + composite {100 * st['bloom_v_composite'] / s:.1f} %.\n")
