@@ -66,7 +66,7 @@ extern "C" int bhr_create(const bhr_config* cfg, bhr_ctx** out) {
     CREATE_CHECK(cudaMemset(ctx->retrace_queue, 0, plane * (sizeof(unsigned long long) + sizeof(int))));
     CREATE_CHECK(cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, cfg->device));
     ctx->persistent = 1;
-    ctx->pblock_big = 1;
+    ctx->pblock_big = 0;        // 768 (512 with differentials) threads per persistent block: measured best at every size
     // [0] re-trace queue tail, [1] band count, [2] band head, [3] tile counter, [4..5] u64 step total
     CREATE_CHECK(cudaMalloc(&ctx->d_queue_count, 8 * sizeof(unsigned int)));
     CREATE_CHECK(cudaMemset(ctx->d_queue_count, 0, 8 * sizeof(unsigned int)));

@@ -8,9 +8,10 @@ from black_hole_renderer_b200 import Renderer
 from black_hole_renderer_b200.driver import compute_disk_texture_resolution
 key, vals = sys.argv[1], [float(v) for v in sys.argv[2:4]]
 res = sys.argv[4] if len(sys.argv) > 4 else "fhd"
+kw = dict(anti_alias="lod_radius", disk_tilt=20.0, lens_flare=True) if len(sys.argv) > 5 and sys.argv[5] == "aa" else {}
 W, H = RESOLUTIONS[res]; pov, fov = [6, 0, 0.5], 90
 n_phi, n_r = compute_disk_texture_resolution(W, H, pov, fov, 2.0, 15.0)
-r = Renderer(W, H, synthetic_skybox(), synthetic_disk_texture(n_r, n_phi))
+r = Renderer(W, H, synthetic_skybox(), synthetic_disk_texture(n_r, n_phi), **kw)
 for _ in range(3): r.render_device(pov, fov)
 for rep in range(3):
     for v in vals:

@@ -7,8 +7,8 @@ set -x
 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-other-configs > gpurun_out/${TAG}_bench_plain.log 2> gpurun_out/${TAG}_bench_plain.err || exit 1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/${TAG}_launches.csv \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-other-configs > gpurun_out/${TAG}_ncu_launches.log 2>&1
-BIG=1 python tools/prof_fhd.py fhd 0 3 > gpurun_out/${TAG}_prof_plain.log 2>&1 || exit 1
-BIG=1 ncu --set full --clock-control none --import-source on -k regex:'raymarch_persistent|band_list|retrace' -s 6 -c 3 \
+python tools/prof_fhd.py fhd 0 3 > gpurun_out/${TAG}_prof_plain.log 2>&1 || exit 1
+ncu --set full --clock-control none --import-source on -k regex:'raymarch_persistent|band_list|retrace' -s 6 -c 3 \
     -o gpurun_out/${TAG}_raymarch -f python tools/prof_fhd.py fhd 0 3 > gpurun_out/${TAG}_ncu_raymarch.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:'bloom|composite' -s 6 -c 3 \
     -o gpurun_out/${TAG}_post -f python tools/prof_fhd.py fhd 0 3 > gpurun_out/${TAG}_ncu_post.log 2>&1
