@@ -297,10 +297,14 @@ def main():
     torch.cuda.synchronize()
     for s in range(args.steps):
         flush.zero_()
+        # the library's own per-stage timing events (instrumentation, five per frame) are recorded on
+        # every fourth frame only -- they feed stage_ms / the roofline; the step timing is evs[]
+        sampled = s % 4 == 3 or s == args.steps - 1
+        r.set_option("stage_timing", 1 if sampled else 0)
         evs[s][0].record(stream)
         r.render_device(camera_of(args.warmup + s), FOV)
         evs[s][1].record(stream)
-        if s % 4 == 3 or s == args.steps - 1:      # stage timers of the latest frame (events already recorded)
+        if sampled:                                # stage timers of the latest frame (events already recorded)
             evs[s][1].synchronize()
             ms = r.last_stage_ms()
             for k in ("ray_march", "bloom_h", "bloom_v_composite"):
@@ -310,6 +314,7 @@ def main():
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    r.set_option("stage_timing", 0)               # off for the end-to-end and video blocks below
     ms_step = sum(a.elapsed_time(b) for a, b in evs) / args.steps
     t = torch.tensor([ms_step], dtype=torch.float64, device="cuda")
     if world > 1:

@@ -79,6 +79,7 @@ extern "C" int bhr_create(const bhr_config* cfg, bhr_ctx** out) {
     ctx->sync_extend = 0.1;
     ctx->strict_warps = 32;
     ctx->band_box = 1;
+    ctx->stage_timing = 1;
     CREATE_CHECK(cudaMemset(ctx->bg, 0, plane * 3 * sizeof(float)));
     CREATE_CHECK(cudaMemset(ctx->disk, 0, plane * 3 * sizeof(float)));
     CREATE_CHECK(cudaMemset(ctx->hblur, 0, plane * 3 * sizeof(float)));
@@ -113,6 +114,7 @@ extern "C" void bhr_destroy(bhr_ctx* ctx) {
     for (int k = 0; k < 12; ++k) if (ctx->band_ev[k]) cudaEventDestroy(ctx->band_ev[k]);
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
     if (ctx->copy_done) cudaEventDestroy(ctx->copy_done);
+    if (ctx->frame_done) cudaEventDestroy(ctx->frame_done);
     if (ctx->h_entities) cudaFreeHost(ctx->h_entities);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     free(ctx);
@@ -151,6 +153,7 @@ extern "C" int bhr_set_option(bhr_ctx* ctx, const char* key, double value) {
     if (ctx && !strcmp(key, "sync_extend")) { ctx->sync_extend = value; return BHR_OK; }
     if (ctx && !strcmp(key, "sync_min_bytes")) { ctx->sync_min_bytes = value; return BHR_OK; }
     if (ctx && !strcmp(key, "planar")) { ctx->planar = (int)value; return BHR_OK; }
+    if (ctx && !strcmp(key, "stage_timing")) { ctx->stage_timing = (int)value != 0; return BHR_OK; }
     if (ctx && !strcmp(key, "band_box")) { ctx->band_box = (int)value; return BHR_OK; }
     if (ctx && !strcmp(key, "strict_warps")) { ctx->strict_warps = (int)value; return BHR_OK; }
     if (ctx) snprintf(ctx->err, sizeof(ctx->err), "unknown option %s", key);
@@ -169,15 +172,15 @@ extern "C" int bhr_render_rows_stage1(bhr_ctx* ctx, const bhr_camera* cam, uint3
     int rc = check_rows(ctx, row0, row1);
     if (rc) return rc;
     BHR_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
-    BHR_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+    if (ctx->stage_timing) BHR_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
     rc = bhr_launch_raymarch(ctx, cam, flags, row0, row1);
     if (rc) return rc;
-    BHR_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+    if (ctx->stage_timing) BHR_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
     if (!(flags & BHR_SKIP_BLOOM)) {
         rc = bhr_launch_bloom_h(ctx, row0, row1);
         if (rc) return rc;
     }
-    BHR_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+    if (ctx->stage_timing) BHR_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
     return BHR_OK;
 }
 
@@ -196,11 +199,11 @@ extern "C" int bhr_render_rows_stage2(bhr_ctx* ctx, uint32_t flags, int row0, in
     if (!ctx) return BHR_ERR_INVALID;
     int rc = check_rows(ctx, row0, row1);
     if (rc) return rc;
-    BHR_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
+    if (ctx->stage_timing) BHR_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
     rc = bhr_launch_bloom_v_composite(ctx, flags, row0, row1, flare_sums);
     if (rc) return rc;
-    BHR_CUDA(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
-    ctx->ev_valid = 1;
+    if (ctx->stage_timing) BHR_CUDA(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
+    ctx->ev_valid = ctx->stage_timing;
     return BHR_OK;
 }
 
@@ -221,11 +224,12 @@ static int render_enqueue(bhr_ctx* ctx, const bhr_camera* cam, uint32_t flags, f
     }
     rc = bhr_render_rows_stage2(ctx, flags, 0, ctx->H, psums);
     if (rc) return rc;
-    BHR_CUDA(ctx, cudaEventRecord(ctx->ev[5], ctx->stream));
     cudaStream_t cs = ctx->stream;
     if (copy_stream && (out_f32 || out_u8)) {
         cs = copy_stream;
-        BHR_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->ev[5], 0));
+        if (!ctx->frame_done) BHR_CUDA(ctx, cudaEventCreateWithFlags(&ctx->frame_done, cudaEventDisableTiming));
+        BHR_CUDA(ctx, cudaEventRecord(ctx->frame_done, ctx->stream));
+        BHR_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->frame_done, 0));
     }
     const size_t n3 = (size_t)ctx->W * ctx->H * 3;
     if (out_f32) BHR_CUDA(ctx, cudaMemcpyAsync(out_f32, ctx->final_f32, n3 * sizeof(float), cudaMemcpyDeviceToHost, cs));
@@ -445,7 +449,7 @@ extern "C" int bhr_last_retrace_count(bhr_ctx* ctx, uint32_t* out) {
 
 extern "C" int bhr_last_stage_ms(bhr_ctx* ctx, float out[5]) {
     if (!ctx || !out) return BHR_ERR_INVALID;
-    if (!ctx->ev_valid) BHR_FAIL(ctx, BHR_ERR_STATE, "no frame rendered yet");
+    if (!ctx->ev_valid) BHR_FAIL(ctx, BHR_ERR_STATE, "no frame rendered with stage timing on (option \"stage_timing\")");
     BHR_CUDA(ctx, cudaEventSynchronize(ctx->ev[4]));
     BHR_CUDA(ctx, cudaEventElapsedTime(&out[0], ctx->ev[0], ctx->ev[1]));   // ray march
     BHR_CUDA(ctx, cudaEventElapsedTime(&out[1], ctx->ev[1], ctx->ev[2]));   // bloom H

@@ -104,6 +104,8 @@ struct bhr_ctx {
     // completion event per band, and "this launch continues a frame: keep the RK4 step total"
     int sync_bands; double sync_min_bytes, sync_extend; cudaEvent_t band_ev[12]; int keep_step_total;
     int strict_warps, band_box, planar;
+    int stage_timing;                  // record the per-stage timing events (instrumentation; each costs ~1.5 us of stream time)
+    cudaEvent_t frame_done;            // orders the copy stream behind the composite (no timing)
     int ev_valid;
     float tint[3];
 };

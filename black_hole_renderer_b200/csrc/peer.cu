@@ -167,11 +167,11 @@ extern "C" int bhr_render_tiled_peer(bhr_ctx* ctx, const bhr_camera* cam, uint32
     peer.final_u8 = own_egress ? nullptr : ctx->peer_final_u8[0];
     peer.flare_params = flare ? ctx->d_flare_params : nullptr;
     peer.before_composite = own_egress ? nullptr : wait_consumed;
-    BHR_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
+    if (ctx->stage_timing) BHR_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
     rc = bhr_launch_bloom_v_composite_ex(ctx, flags, row0, row1, nullptr, &peer);
     if (rc) return rc;
-    BHR_CUDA(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
-    ctx->ev_valid = 1;
+    if (ctx->stage_timing) BHR_CUDA(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
+    ctx->ev_valid = ctx->stage_timing;
     const size_t row3 = (size_t)ctx->W * 3;
     if (own_egress) {
         rc = wait_consumed(ctx);                 // the host frame still holds s - 1 until rank 0's caller returns for more

@@ -133,6 +133,8 @@ def render_video(renderer, width, height, n_frames, fps, output_path, fov, stati
     if barrier:
         barrier()
     os.makedirs(temp_dir, exist_ok=True)
+    if hasattr(renderer, "set_option"):
+        renderer.set_option("stage_timing", 0)      # no per-stage timing events in the frame loop
 
     # PNG encoding is host work outside the render path and the wall-clock limit of a video run
     # (about 50 ms per 1080p frame and core at zlib level 1): use the host's cores for it

@@ -98,7 +98,8 @@ int bhr_version(void);
  * one block per SM with work queues, strict and fast rays on disjoint SMs; "pblock_big";
  * "strict_warps" = n: warps per strict block that trace photon-ring batches (default: all; fewer
  * spreads them over more SMs -- lower latency of a small ring tile, idle warps meanwhile);
- * "band_box" = 1 (default): the band-list kernel scans only the photon ring's bounding box;
+ * "stage_timing" = 1 (default): record the CUDA events bhr_last_stage_ms reads (five timing events
+ * per frame, ~1.5 us of stream time each; video loops switch them off); "band_box" = 1 (default): the band-list kernel scans only the photon ring's bounding box;
  * "sync_bands" / "sync_min_bytes": row bands of synchronous host frames, see bhr_render */
 int bhr_set_option(bhr_ctx* ctx, const char* key, double value);
 /* pinned host memory so that frame read-back DMA needs no staging copy */
