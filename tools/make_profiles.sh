@@ -15,6 +15,7 @@ ncu --set full --clock-control none --import-source on -k regex:'bloom|composite
 python tools/prof_fhd.py 4k 0 3 aa > gpurun_out/${TAG}_prof_4k_plain.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:'raymarch_persistent' -s 1 -c 1 \
     -o gpurun_out/${TAG}_raymarch_4k_aa -f python tools/prof_fhd.py 4k 0 3 aa > gpurun_out/${TAG}_ncu_raymarch_4k.log 2>&1
+[ -n "$SKIP_TEXTURE" ] && exit 0
 python tools/video_breakdown.py > gpurun_out/${TAG}_video_plain.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:'background_kernel|entity_accumulate|compose_kernel|stats_rows|select_hist' -s 8 -c 6 \
     -o gpurun_out/${TAG}_texture -f python tools/video_breakdown.py > gpurun_out/${TAG}_ncu_texture.log 2>&1

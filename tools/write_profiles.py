@@ -50,7 +50,7 @@ def launches(csv_in, md_out, bench_log):
         v = v / 1000 if r[iu] == 'ns' else v * 1000 if r[iu] == 'ms' else v
         agg.setdefault(r[ik].split('(')[0].replace('void ', '').replace('<unnamed>::', ''), []).append(v)
     bench = json.loads(open(os.path.join(G, bench_log)).read().strip().splitlines()[-1])
-    frame = ['band_list_kernel', 'raymarch_persistent<0, 896, 0>', 'retrace_kernel<0>', 'bloom_h_kernel', 'bloom_v_kernel<0>', 'composite_kernel<1, 4, 0>']
+    frame = ['band_list_kernel', 'raymarch_persistent<0, 768, 0>', 'retrace_kernel<0>', 'bloom_h_kernel', 'bloom_v_kernel<0>', 'composite_kernel<1, 4, 0>']
     med = lambda v: sorted(v)[len(v) // 2]      # (median: the banded synchronous frames of the e2e block launch the same kernels on row bands)
     tot = sum(med(agg[k]) for k in frame if k in agg)
     with open(os.path.join(P, md_out), "w") as f:
