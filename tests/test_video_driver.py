@@ -100,3 +100,23 @@ def test_static_camera_and_sharding(tmp_path):
     assert sorted(prog["completed"]) == list(range(150))
     # every rank recomputes the statistics on the first frame of each block it owns
     assert a.stats_calls == 1 + 2 and b.stats_calls == 1 + 1
+
+
+def test_encode_png_round_trips_through_pil(tmp_path):
+    """driver.encode_png (filter 0 + zlib, the frame files of a video run) decodes to the same
+    pixels with an independent PNG reader: ragged sizes, every zlib level, extreme values."""
+    from PIL import Image
+    from black_hole_renderer_b200.driver import encode_png
+    rng = np.random.default_rng(3)
+    for (h, w), level in (((1, 1), 1), ((7, 13), 0), ((64, 48), 1), ((33, 257), 6), ((360, 640), 1)):
+        img = rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8)
+        img[0, 0] = (0, 255, 0)
+        img[::3] = np.minimum(img[::3], 8)                 # smooth, compressible rows too
+        path = tmp_path / f"t_{h}x{w}.png"
+        path.write_bytes(encode_png(img, level))
+        back = Image.open(path)
+        assert back.mode == "RGB" and back.size == (w, h)
+        assert np.array_equal(np.array(back), img)
+    sliced = rng.integers(0, 256, size=(20, 30, 3), dtype=np.uint8)[::2, ::3]      # non-contiguous input
+    (tmp_path / "s.png").write_bytes(encode_png(sliced))
+    assert np.array_equal(np.array(Image.open(tmp_path / "s.png")), sliced)
