@@ -281,7 +281,7 @@ static int plan_bands(const bhr_ctx* ctx, const bhr_camera* cam, uint32_t flags,
     if (H - yb < min_rows) yb = H;
     int n = 0;
     bands[n][0] = ya; bands[n][1] = yb; ++n;
-    const int pieces = ctx->sync_bands;
+    const int pieces = ctx->sync_bands < 5 ? ctx->sync_bands : 5;      // 1 + 2 * 5 bands fit max_bands
     // pieces next to the ring first: together with it they complete the rows around its edges
     for (int side = 0; side < 2; ++side) {
         const int lo = side == 0 ? 0 : yb, hi = side == 0 ? ya : H;
