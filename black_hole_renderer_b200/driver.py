@@ -32,19 +32,23 @@ def save_image(image, path):
 
 
 def encode_png(img_u8, level=1):
-    """8-bit RGB (H, W, 3) -> PNG bytes: filter type 0 on every scanline, one zlib stream.
+    """8-bit RGB (H, W, 3) -> PNG bytes: filter type 1 (Sub) on every scanline, one zlib stream.
 
     The frame files of a video run are an intermediate for the muxer (render.py:4462-4467), so speed
-    matters more than size: without PIL's per-row filter search the same zlib level costs half the
-    time (66 instead of 133 ms per 1080p frame and core), and zlib / crc32 release the GIL, so a
-    thread pool scales over the host cores.  Any PNG reader decodes it to the same pixels."""
+    matters more than size.  PIL searches a filter per row; a fixed Sub filter (difference to the
+    pixel on the left, one wrapping uint8 subtraction over the frame, 4 ms) makes a rendered frame
+    both faster to deflate and a third smaller than unfiltered rows, and costs less than half of
+    PIL's time at the same zlib level.  zlib / crc32 release the GIL, so a thread pool scales over
+    the host cores.  Any PNG reader decodes the file to the same pixels."""
     import struct
     import zlib
     h, w, c = img_u8.shape
     assert c == 3 and img_u8.dtype == np.uint8
+    rows = img_u8.reshape(h, w * 3)
     raw = np.empty((h, w * 3 + 1), np.uint8)
-    raw[:, 0] = 0                                  # filter type of the scanline: None
-    raw[:, 1:] = img_u8.reshape(h, w * 3)
+    raw[:, 0] = 1                                  # filter type of the scanline: Sub
+    raw[:, 1:] = rows
+    raw[:, 4:] -= rows[:, :-3]                     # uint8 arithmetic wraps modulo 256, as the filter requires
     data = zlib.compress(memoryview(raw).cast("B"), level)
 
     def chunk(tag, payload):

@@ -103,7 +103,7 @@ def test_static_camera_and_sharding(tmp_path):
 
 
 def test_encode_png_round_trips_through_pil(tmp_path):
-    """driver.encode_png (filter 0 + zlib, the frame files of a video run) decodes to the same
+    """driver.encode_png (Sub-filtered scanlines + zlib, the frame files of a video run) decodes to the same
     pixels with an independent PNG reader: ragged sizes, every zlib level, extreme values."""
     from PIL import Image
     from black_hole_renderer_b200.driver import encode_png
