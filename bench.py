@@ -13,9 +13,23 @@ time.  `value` is timed with CUDA events on the launching stream with the result
 `e2e` is the same frame through Renderer.render() into a pinned HOST buffer (D2H inside the
 timed region).  L2 is flushed between timed steps (outside the event brackets).
 
+Further blocks of the same JSON line (each timed on its own, after the headline):
+  orbit_video_full  BASELINE.json configs[4] as a WHOLE JOB: all 3600 frames of `render.py --video
+                    --orbit -r fhd` through driver.run_video_frames (the CLI's frame loop: 60-frame
+                    blocks dealt round-robin, every rank ticks every frame, PNG / x264 off);
+  tiled_4k          (N > 1) BASELINE.json configs[2]: one 4K frame (ray differentials + mip LOD, tilt
+                    20, flare) split into row tiles -- NCCL path (halo send/recv, flare all-reduce,
+                    gather to rank 0) and peer-memory path (csrc/peer.cu), equal and cost-balanced
+                    tiles, rank-0 and distributed egress -- each compared with the one-GPU frame;
+                    a tiled frame that differs beyond the flare-sum rounding makes the run FAIL;
+  e2e.d2h           raw pinned D2H bandwidth of one frame-sized copy per rank, alone and with all
+                    ranks copying at once (separates the host fabric from the renderer).
+
 `--impl reference` times the reference's CPU implementation of the same path on the host cores:
 Taichi is not installable here, so it is the oracle port (oracle/bhr_oracle.c,
-OpenMP over all host threads) -- labelled kind "port".
+OpenMP over all host threads) -- labelled kind "port".  Both arms render the same scene: skybox
+seed 42 and the lifecycle disk texture at t = 0 (the CPU arm builds it with the oracle's
+restatement of the texture pipeline).
 """
 import argparse
 import json
@@ -91,58 +105,221 @@ def cpu_port_frame(width, height, sky, tex, threads=None):
     return time.perf_counter() - t0, r["total_steps"], O.lib().orc_num_threads()
 
 
-def orbit_video_block(r, n_r, n_phi, rank, world, dist, torch, block=60, n_frames_total=3600):
-    """Steady-state frames/s of the orbit video path (render.py --video --orbit --n_frames 3600
-    -r fhd).  Frames are dealt to ranks in 60-frame blocks (the statistics cadence); every rank
-    replays the host lifecycle ticks of ALL frames.  Timed: one full cycle of 60 x world frames
-    per rank, starting at the rank's own block (the ticks up to there run before the clock starts):
-    60 frames of background + entity layer + [statistics on the block's first frame] + compose +
-    mips + ray march + bloom + composite with the 8-bit frame copied to pinned host memory, then
-    the ticks of the other ranks' 60 x (world - 1) frames, which the host runs while the device
-    drains the pipeline.  PNG / x264 encoding is excluded."""
-    from black_hole_renderer_b200.driver import frame_owner, orbit_camera
-    from black_hole_renderer_b200.lifecycle import advance_lifecycle_frame, init_lifecycle_system
-    factories = init_lifecycle_system(r, n_r, n_phi, seed=42)
-    depth = 7                                         # frames the host may run ahead (8 completion slots)
-    bufs = [r.pinned_frame(np.uint8) for _ in range(depth + 1)]
-    dt = 0.1
-    for frame in range(block * rank):                 # untimed: bring the lifecycle to my block
-        for f in factories.values():
-            f.tick(now=frame * dt, dt=dt)
-    r.render_u8(POV, FOV, out=bufs[0])
+def lifecycle_texture_cpu(n_r, n_phi, r_inner=2.0, r_outer=15.0):
+    """The disk texture of `render.py` single frames (lifecycle system, seed 42, t = 0) built WITHOUT
+    the GPU: host factories + the oracle's restatement of background / entity layer / statistics /
+    compose (render.py:4079-4153).  For the CPU arms, so that both arms render the same scene."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as O
+    from black_hole_renderer_b200.lifecycle import make_factories
+    rng = np.random.default_rng(42)
+    az_freq, az_shear = int(rng.integers(2, 5)), float(rng.uniform(2.0, 4.0))
+    factories = make_factories(r_inner, r_outer, n_r, n_phi, seed=42)      # (seeded and pre-populated)
+    edge, omega = O.edge_alpha(n_r), O.omega_rows(n_r, r_inner, r_outer)
+    comp = np.zeros((13, n_r, n_phi), dtype=np.float32)
+    for first in (True, False):              # _init_lifecycle_system, then _advance_lifecycle_frame(t=0, dt=0)
+        if not first:
+            for f in factories.values():
+                f.tick(now=0.0, dt=0.0)
+        O.generate_background(comp, az_freq, az_shear, r_inner, r_outer, 0.0)
+        comp[5:11] = O.accumulate_entities(factories, 0.0, n_r, n_phi, omega)
+        stats, rows = O.interactive_stats(comp, edge)
+        tex = O.compose_texture(comp, omega, edge, stats, rows)
+    return tex
+
+
+def orbit_video_full(r, rank, world, dist, torch, n_frames=3600, block=60):
+    """BASELINE.json configs[4] as a whole job: `render.py --video --orbit --n_frames 3600 --fps 36
+    -r fhd` through the CLI's own frame loop (driver.run_video_frames, render.py:4437-4458): frames
+    dealt to ranks in 60-frame blocks (the statistics cadence), every rank replays the host
+    lifecycle ticks of ALL frames and, for its own frames, runs background + entity layer +
+    [statistics on a block's first frame] + compose + mips + ray march + bloom + composite and
+    copies the 8-bit frame to pinned host memory.  PNG / x264 encoding off (host I/O).  Timed from
+    a barrier to the moment the slowest rank has its last frame in host memory."""
+    from black_hole_renderer_b200.driver import frame_owner, run_video_frames
+    per_rank = [sum(1 for f in range(n_frames) if frame_owner(f, world, block) == k) for k in range(world)]
+    r.set_option("stage_timing", 0)
+    t_setup = time.perf_counter()
+    from black_hole_renderer_b200.lifecycle import init_lifecycle_system
+    factories = init_lifecycle_system(r, r.dtex_h, r.dtex_w, seed=42)
+    r.synchronize()
+    setup_s = time.perf_counter() - t_setup
+    launches0 = r.launch_count()
     torch.cuda.synchronize()
     if dist:
         dist.barrier()
     t0 = time.perf_counter()
-    issued, in_flight = 0, []
-    for frame in range(block * rank, block * rank + block * world):
-        t = frame * dt
-        if frame_owner(frame, world, block) != rank:
-            for f in factories.values():
-                f.tick(now=t, dt=dt)
-            continue
-        # pipelined like driver.render_video: the host runs up to `depth` frames ahead
-        advance_lifecycle_frame(r, factories, t, dt, recompute_stats=(frame % block == 0))
-        slot = issued % (depth + 1)
-        r.render_u8_async(orbit_camera(POV, frame, n_frames_total, 360.0), FOV, bufs[slot], slot)
-        in_flight.append(slot)
-        if len(in_flight) > depth:
-            r.wait_frame(in_flight.pop(0))
-        issued += 1
-    for slot in in_flight:
-        r.wait_frame(slot)
+    rendered = run_video_frames(r, n_frames, FOV, POV, True, 360.0, 0.1, rank, world, factories=factories, depth=7)
     torch.cuda.synchronize()
     sec = time.perf_counter() - t0
-    tt = torch.tensor([sec], dtype=torch.float64, device="cuda")
+    launches = r.launch_count() - launches0
+    assert rendered == per_rank[rank], (rendered, per_rank)
+    tt = torch.tensor([sec, setup_s], dtype=torch.float64, device="cuda")
     if dist:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    sec = float(tt.item())
-    return {"frames_per_s": block * world / sec, "frames": block * world, "seconds_max_over_ranks": sec,
-            "ms_per_frame_per_gpu": 1e3 * sec / block,
-            "includes": "one steady-state cycle per rank: host lifecycle ticks of all 60 x N frames, and for the rank's own "
-                        "60 frames background + entity + compose + mips kernels, statistics on the block's first frame, "
-                        "render, 8-bit frame D2H to pinned memory",
-            "excludes": "PNG / x264 encoding (host I/O)", "sharding": f"{block}-frame blocks round-robin, no collective"}
+    sec, setup_s = (float(v) for v in tt.tolist())
+    return {"frames": n_frames, "frames_per_s": n_frames / sec, "seconds_max_over_ranks": sec,
+            "per_rank_frames": per_rank, "ms_per_frame_per_gpu": 1e3 * sec / max(per_rank),
+            "balance_ceiling": n_frames / (world * max(per_rank)),
+            "setup_seconds": setup_s, "frames_per_s_including_setup": n_frames / (sec + setup_s),
+            "gpu_launches_rank0": launches,
+            "includes": "the whole 3600-frame job of render.py --video --orbit -r fhd: host lifecycle ticks of all frames on every "
+                        "rank; for a rank's own frames background + entity + compose + mips kernels, statistics on each block's "
+                        "first frame, render, 8-bit frame D2H to pinned memory",
+            "excludes": "PNG / x264 encoding (host I/O); setup (factory seeding, first texture) reported separately",
+            "sharding": f"{block}-frame blocks round-robin, no collective"}
+
+
+def d2h_probe(r, torch, dist, rank, world, nbytes, reps=8):
+    """Raw D2H bandwidth of one frame-sized pinned copy (GB/s): every rank alone (the others idle)
+    and all ranks at once.  Separates what the host fabric can take from what the renderer does."""
+    import ctypes as C
+    from black_hole_renderer_b200 import _lib as L
+    dev_ptr, _ = r.device_buffer(L.BUF_FINAL)
+    host = r.pinned_frame(np.float32)
+    assert host.nbytes >= nbytes
+    cudart = torch.cuda.cudart()
+    stream = torch.cuda.current_stream()
+
+    def one_round():
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            err = cudart.cudaMemcpyAsync(host.ctypes.data, dev_ptr, nbytes, 2, stream.cuda_stream)   # 2 = cudaMemcpyDeviceToHost
+        e1.record(stream)
+        e1.synchronize()
+        return nbytes * reps / (e0.elapsed_time(e1) * 1e-3) / 1e9
+
+    one_round()
+    alone = [0.0] * world
+    for k in range(world):
+        if dist:
+            dist.barrier()
+        if k == rank:
+            alone[k] = one_round()
+    if dist:
+        dist.barrier()
+    together = one_round()
+    t = torch.tensor(alone + [0.0] * world, dtype=torch.float64, device="cuda")
+    t[world + rank] = together
+    if dist:
+        dist.all_reduce(t)
+    v = t.tolist()
+    return {"bytes": nbytes, "alone_gbs_per_rank": [round(x, 2) for x in v[:world]],
+            "concurrent_gbs_per_rank": [round(x, 2) for x in v[world:]],
+            "concurrent_gbs_total": round(sum(v[world:]), 2)}
+
+
+def tiled_4k(Renderer, sky, rank, world, local, dist, torch, frames=8):
+    """BASELINE.json configs[2]: one 4K frame (anti_alias lod_radius, tilt 20, lens flare, lifecycle
+    texture 832 x 5824) row-tiled over the ranks; 8-bit frame in rank 0's host memory at the end of
+    every frame.  Times (ms/frame): CUDA events on rank 0's stream around `frames` back-to-back
+    frames -- rank 0's stream ends with the gather / the wait for every tile, so its event span
+    covers all ranks -- next to the host clock from a barrier to the last synchronised frame (max
+    over ranks).  Every variant's last frame is compared with the one-GPU frame; the flare centroid
+    is summed per tile, so a handful of last-bit differences is the allowance, anything more FAILS
+    the run."""
+    from black_hole_renderer_b200 import dist as D
+    from black_hole_renderer_b200.driver import compute_disk_texture_resolution
+    from black_hole_renderer_b200.lifecycle import advance_lifecycle_frame, init_lifecycle_system
+    W, H = RES["4k"]
+    n_phi, n_r = compute_disk_texture_resolution(W, H, POV, FOV, 2.0, 15.0)
+    r = Renderer(W, H, sky, np.zeros((n_r, n_phi, 4), np.float32), anti_alias="lod_radius", disk_tilt=20.0,
+                 lens_flare=True, cuda_device=local)
+    stream = torch.cuda.current_stream()
+    r.set_stream(stream.cuda_stream)
+    r.set_option("stage_timing", 0)
+    factories = init_lifecycle_system(r, n_r, n_phi, seed=42)
+    advance_lifecycle_frame(r, factories, t=0.0, dt=0.0, recompute_stats=True)
+    r.synchronize()
+    out = {"workload": "render.py -r 4k --anti_alias lod_radius --disk_tilt 20 --lens_flare (BASELINE.json configs[2]), "
+                       "lifecycle disk texture at t=0, 8-bit frame to rank 0's host memory every frame",
+           "resolution": [W, H], "disk_texture": [n_r, n_phi], "frames_timed": frames, "n_gpus": world}
+
+    def timed(fn):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for _ in range(frames):
+            frame = fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        host_ms = (time.perf_counter() - t0) * 1e3 / frames
+        t = torch.tensor([e0.elapsed_time(e1) / frames, host_ms], dtype=torch.float64, device="cuda")
+        if dist:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, host_ms = t.tolist()
+        return frame, dev_ms, host_ms
+
+    # the one-GPU frame (rank 0 alone; the others wait) -- reference pixels and the strong-scaling base
+    single = None
+    if rank == 0:
+        pinned = r.pinned_frame(np.uint8)
+        for _ in range(2):
+            r.render_u8(POV, FOV, out=pinned)
+        t0 = time.perf_counter()
+        for _ in range(frames):
+            r.render_u8(POV, FOV, out=pinned)
+        out["single_gpu_ms"] = (time.perf_counter() - t0) * 1e3 / frames
+        single = pinned.copy()
+    if world == 1:
+        r.close()
+        return out
+    dist.barrier()
+
+    def compare(name, frame):
+        if rank != 0:
+            return
+        d = np.abs(frame.astype(np.int16) - single.astype(np.int16))
+        out[name]["max_abs_diff"] = int(d.max())
+        out[name]["differing_pixels_vs_single_gpu"] = int((d.max(axis=-1) > 0).sum())
+
+    variants = [("nccl", lambda: D.render_tiled(r, POV, FOV, rank=rank, world_size=world, want_u8=True, copy=False))]
+    frame, dev_ms, host_ms = timed(variants[0][1])
+    out["nccl"] = {"ms": dev_ms, "host_clock_ms": host_ms,
+                   "path": "stage 1 -> ncclSend/Recv halos of the H-blurred layer -> ncclAllReduce of the flare sums (device) "
+                           "-> stage 2 -> tiles received into rank 0's frame buffer -> one D2H"}
+    compare("nccl", frame)
+    D.attach_peers(r, rank, world)
+    frame, dev_ms, host_ms = timed(lambda: D.render_tiled_peer(r, POV, FOV))
+    out["peer"] = {"ms": dev_ms, "host_clock_ms": host_ms,
+                   "path": "csrc/peer.cu: V pass loads halo rows from the neighbours' HBM, composite stores into rank 0's "
+                           "buffers, release/acquire flags; equal-height tiles; rank 0 copies the frame out"}
+    compare("peer", frame)
+    bounds = D.balance_tiles(r, POV, FOV, rank, world)
+    frame, dev_ms, host_ms = timed(lambda: D.render_tiled_peer(r, POV, FOV))
+    out["peer_balanced"] = {"ms": dev_ms, "host_clock_ms": host_ms, "tile_bounds": bounds,
+                            "path": "the same with tile heights balanced by RK4 evaluations per row (dist.balance_tiles)"}
+    compare("peer_balanced", frame)
+    D.attach_shared_frame(r, rank, world)
+    frame, dev_ms, host_ms = timed(lambda: D.render_tiled_peer(r, POV, FOV))
+    out["peer_balanced_egress"] = {"ms": dev_ms, "host_clock_ms": host_ms,
+                                   "path": "balanced tiles + distributed egress: every rank copies its own rows into one shared, "
+                                           "page-locked host frame over its own PCIe link"}
+    compare("peer_balanced_egress", frame)
+    frame, dev_ms, host_ms = timed(lambda: D.render_tiled(r, POV, FOV, rank=rank, world_size=world, want_u8=True, copy=False,
+                                                          bounds=bounds))
+    out["nccl_balanced_egress"] = {"ms": dev_ms, "host_clock_ms": host_ms,
+                                   "path": "NCCL halos + all-reduce, balanced tiles, every rank's own D2H into the shared host frame"}
+    compare("nccl_balanced_egress", frame)
+    dist.barrier()
+    ok = True
+    if rank == 0:
+        best = min(out[k]["ms"] for k in ("nccl", "peer", "peer_balanced", "peer_balanced_egress", "nccl_balanced_egress"))
+        out["best_ms"] = best
+        out["strong_scaling_efficiency_vs_single_gpu"] = out["single_gpu_ms"] / (world * best)
+        limit = max(8, int(1e-5 * W * H))
+        for k in ("nccl", "peer", "peer_balanced", "peer_balanced_egress", "nccl_balanced_egress"):
+            ok = ok and out[k]["max_abs_diff"] <= 1 and out[k]["differing_pixels_vs_single_gpu"] <= limit
+        out["parity_ok"] = bool(ok)
+        out["parity_rule"] = f"per variant: max |delta| <= 1 (8-bit) and <= {limit} differing pixels vs the one-GPU frame"
+    r.close()
+    return out, ok
 
 
 def other_configs(Renderer, sky, peak, stream, frames=5):
@@ -150,17 +327,17 @@ def other_configs(Renderer, sky, peak, stream, frames=5):
     r_max 30): best-of-`frames` device time of one frame with the result left in HBM, the ray
     march's share of it and its fraction of the measured FP32 peak (SURVEY.md 8d flop counts)."""
     import torch
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from util import synthetic_disk_texture
     from black_hole_renderer_b200.driver import compute_disk_texture_resolution
+    from black_hole_renderer_b200.lifecycle import advance_lifecycle_frame, init_lifecycle_system
     out = {}
     cases = {"configs[2] 4k anti_alias=lod_radius disk_tilt=20 lens_flare": ("4k", dict(anti_alias="lod_radius", disk_tilt=20.0, lens_flare=True), FLOP_PER_STEP_DIFF),
              "configs[3] fhd step_size=0.02 r_max=30": ("fhd", dict(step_size=0.02, r_max=30.0), FLOP_PER_STEP)}
     for name, (res, kw, flop) in cases.items():
         W, H = RES[res]
         n_phi, n_r = compute_disk_texture_resolution(W, H, POV, FOV, 2.0, 15.0)
-        r = Renderer(W, H, sky, synthetic_disk_texture(n_r, n_phi), cuda_device=torch.cuda.current_device(), **kw)
+        r = Renderer(W, H, sky, np.zeros((n_r, n_phi, 4), np.float32), cuda_device=torch.cuda.current_device(), **kw)
         r.set_stream(stream.cuda_stream)
+        advance_lifecycle_frame(r, init_lifecycle_system(r, n_r, n_phi, seed=42), t=0.0, dt=0.0, recompute_stats=True)
         best = None
         for i in range(frames + 2):
             r.render_device(POV, FOV)
@@ -171,9 +348,9 @@ def other_configs(Renderer, sky, peak, stream, frames=5):
         steps = r.last_total_steps()
         tf = flop * steps / (best["ray_march"] * 1e-3) / 1e12
         out[name] = {"ms_per_frame": best["total"], "Mrays_per_s": W * H / (best["total"] * 1e-3) / 1e6,
-                     "stage_ms": {k: best[k] for k in ("ray_march", "bloom_h", "bloom_v_composite", "gap")},
+                     "stage_ms": {k: best[k] for k in ("ray_march", "bloom_h", "bloom_v_composite", "flare")},
                      "rk4_steps_per_frame": steps, "ray_march_tflops": tf, "frac_of_fp32_peak": (tf / peak) if peak else None,
-                     "flop_per_step": flop, "disk_texture": "synthetic (texel values do not affect the timing)"}
+                     "flop_per_step": flop, "disk_texture": [n_r, n_phi]}
         r.close()
     return out
 
@@ -206,9 +383,7 @@ def run_reference(args):
         return
     W, H = RES[args.resolution]
     sky, n_r, n_phi = scene_inputs(W, H)
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from util import synthetic_disk_texture
-    tex = synthetic_disk_texture(n_r, n_phi)      # texel values do not affect the CPU timing
+    tex = lifecycle_texture_cpu(n_r, n_phi)       # the same scene as the GPU arm: lifecycle texture at t = 0
     times = []
     all_threads = os.cpu_count() or 1         # torchrun exports OMP_NUM_THREADS=1: use every host thread
     for i in range(args.warmup + args.steps):
@@ -220,13 +395,20 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "Mrays/s", "value": val, "unit": "Mrays/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"render.py -r {args.resolution} default scene, single frame, anti_alias "
-                                   "disabled (BASELINE.json configs[1]); ray march + bloom + composite"},
+            "config": workload_config(args.resolution, W, H, n_r, n_phi, 1, None),
             "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": threads, "kind": "port",
                              "sample": "every step is one full frame on the host cores (OpenMP oracle "
                                        "port; Taichi not installable, SURVEY.md 8c)"},
             "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+def workload_config(resolution, W, H, n_r, n_phi, world, mode):
+    """The `config` object: identical in both arms (same workload string, same scene)."""
+    return {"workload": (f"render.py -r {resolution} default scene (pov 6 0 0.5, fov 90, step 0.1, r_max 10), single "
+                         "frame, anti_alias disabled = BASELINE.json configs[1]; procedural skybox seed 42 + "
+                         "lifecycle disk texture at t=0; ray march + bloom + composite"),
+            "resolution": [W, H], "rays_per_frame": W * H, "disk_texture": [n_r, n_phi]}
 
 
 def main():
@@ -239,17 +421,24 @@ def main():
     ap.add_argument("--mode", default=None, help="raymarch mode override: fast | strict")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true")
+    ap.add_argument("--no-orbit", action="store_true")
+    ap.add_argument("--no-tiled", action="store_true")
+    ap.add_argument("--orbit-frames", type=int, default=3600)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    # host placement first: threads and the pinned frame buffers allocated below follow the affinity
+    from black_hole_renderer_b200 import hostmem
+    placement = hostmem.bind_to_gpu(local)
 
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the render path has no CPU fallback")
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -295,6 +484,7 @@ def main():
     stage = {"ray_march": 0.0, "bloom_h": 0.0, "bloom_v_composite": 0.0}
     total_steps = 0
     torch.cuda.synchronize()
+    launches0 = r.launch_count()
     for s in range(args.steps):
         flush.zero_()
         # the library's own per-stage timing events (instrumentation, five per frame) are recorded on
@@ -312,14 +502,19 @@ def main():
             stage["n"] = stage.get("n", 0) + 1
             total_steps = r.last_total_steps()
     torch.cuda.synchronize()
+    launches = r.launch_count() - launches0
     if world > 1:
         dist.barrier()
     r.set_option("stage_timing", 0)               # off for the end-to-end and video blocks below
     ms_step = sum(a.elapsed_time(b) for a, b in evs) / args.steps
-    t = torch.tensor([ms_step], dtype=torch.float64, device="cuda")
+    t = torch.tensor([ms_step, float(launches)], dtype=torch.float64, device="cuda")
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t.item())
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        ms_step, launches = float(tmax[0].item()), int(t[1].item())
+    else:
+        ms_step, launches = float(t[0].item()), int(t[1].item())
 
     # ---- end to end through the public API: camera in, frame in host memory out ----
     out = r.pinned_frame(np.float32)
@@ -350,13 +545,26 @@ def main():
             r.wait_frame((s - 1) % 2)
     r.wait_frame((args.steps - 1) % 2)
     pipe_ms = (time.perf_counter() - t0) * 1e3 / args.steps
-    t = torch.tensor([pipe_ms], dtype=torch.float64, device="cuda")
+    # ... and as 8-bit frames (what render_image / render_video save: 6.2 MB instead of 24.9 MB)
+    u8 = r.pinned_frame(np.uint8)
+    r.render_u8(camera_of(0), FOV, out=u8)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        r.render_u8(camera_of(args.warmup + s), FOV, out=u8)
+    u8_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    t = torch.tensor([pipe_ms, u8_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    pipe_ms = float(t.item())
+    pipe_ms, u8_ms = (float(v) for v in t.tolist())
+    d2h = d2h_probe(r, torch, dist if world > 1 else None, rank, world, W * H * 12)
 
-    # ---- orbit video (BASELINE.json configs[4]): one 60-frame block per rank, whole per-frame path ----
-    orbit = orbit_video_block(r, n_r, n_phi, rank, world, dist if world > 1 else None, torch)
+    # ---- orbit video (BASELINE.json configs[4]): the whole 3600-frame job ----
+    orbit = None
+    if not args.no_orbit:
+        orbit = orbit_video_full(r, rank, world, dist if world > 1 else None, torch, n_frames=args.orbit_frames)
     clocks = sampler.stop() if sampler else None      # sampled every 20 ms over all the timed regions above
 
     # ---- the other BASELINE.json configurations, device-resident, rank 0 at N = 1 (parity-tested in
@@ -364,9 +572,15 @@ def main():
     other = None
     if world == 1 and not args.no_other_configs:
         other = other_configs(Renderer, sky, peak, stream)
+    # ---- configs[2] row-tiled over the ranks (N > 1); its one-GPU end-to-end number at N = 1 ----
+    tiled, tiled_ok = None, True
+    if not args.no_tiled:
+        res = tiled_4k(Renderer, sky, rank, world, local, dist if world > 1 else None, torch)
+        tiled, tiled_ok = res if isinstance(res, tuple) else (res, True)
 
     if rank != 0:
         if world > 1:
+            dist.barrier()
             dist.destroy_process_group()
         return
     n = stage.pop("n", 1)
@@ -375,18 +589,19 @@ def main():
     flops = FLOP_PER_STEP * total_steps
     achieved = flops / (stage["ray_march"] * 1e-3) / 1e12
     traffic, traffic_src = profiled_traffic()
+    nominal = 148 * 128 * 2 * 1.965e9 / 1e12          # SMs x FP32 lanes x 2 flop x boost clock
+    t_copy_ms = W * H * 12 / (min(d2h["concurrent_gbs_per_rank"]) * 1e9) * 1e3
+    cfg = workload_config(args.resolution, W, H, n_r, n_phi, world, args.mode)
+    cfg.update({"rays_per_step": rays,
+                "multi_gpu": None if world == 1 else "N>1: one orbit-video frame (configs[4] camera path) per rank per "
+                                                     "step, frames sharded, no collective",
+                "l2": "flushed (256 MiB memset) between timed steps, outside the event brackets",
+                "raymarch_mode": args.mode or "default", "host_placement": placement})
     line = {
         "metric": "Mrays/s", "value": rays / (ms_step * 1e-3) / 1e6, "unit": "Mrays/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": (f"render.py -r {args.resolution} default scene (pov 6 0 0.5, fov 90, step 0.1, "
-                                "r_max 10), single frame, anti_alias disabled = BASELINE.json configs[1]; "
-                                "procedural skybox seed 42 + lifecycle disk texture at t=0"
-                                + ("" if world == 1 else "; N>1: one orbit-video frame (configs[4] camera path) "
-                                                        "per rank per step, frames sharded, no collective")),
-                   "resolution": [W, H], "rays_per_step": rays, "disk_texture": [n_r, n_phi],
-                   "l2": "flushed (256 MiB memset) between timed steps, outside the event brackets",
-                   "raymarch_mode": args.mode or "default"},
+        "config": cfg,
         "ms_per_frame": ms_step, "frames_per_s": world / (ms_step * 1e-3),
         "stage_ms": stage, "rk4_steps_per_frame": total_steps,
         "e2e": {"value": rays / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_frame": e2e_ms,
@@ -395,22 +610,32 @@ def main():
                         "frame is finished in 3 row bands (photon-ring rows first) so that a band's D2H overlaps the next band's ray march",
                 "pipelined": {"value": rays / (pipe_ms * 1e-3) / 1e6, "ms_per_frame": pipe_ms,
                               "note": "same frames and bytes through Renderer.render_async / wait_frame (two pinned "
-                                      "buffers): the D2H of frame i overlaps the ray march of frame i + 1"}},
-        "gpu_launches": 6 * args.steps * world,   # band_list, raymarch_persistent, retrace, bloom_h, bloom_v, composite per frame
+                                      "buffers): the D2H of frame i overlaps the ray march of frame i + 1"},
+                "u8": {"value": rays / (u8_ms * 1e-3) / 1e6, "ms_per_frame": u8_ms, "d2h_bytes_per_step": W * H * 3,
+                       "note": "Renderer.render_u8: the 8-bit frame the drivers save (render.py:423, 4463)"},
+                "d2h": d2h,
+                "limiter": ("host D2H bandwidth" if t_copy_ms > ms_step else "render"),
+                "limiter_arithmetic": (f"one {W * H * 12 / 1e6:.1f} MB frame at the slowest rank's concurrent D2H rate "
+                                       f"({min(d2h['concurrent_gbs_per_rank']):.1f} GB/s with all {world} rank(s) copying) = "
+                                       f"{t_copy_ms:.3f} ms vs {ms_step:.3f} ms to render it")},
+        "gpu_launches": launches,                 # counted by the library (bhr_launch_count), all ranks, timed region of `value`
         "roofline": {"bound": "fp32", "kernel": "raymarch_persistent (+ band_list, retrace)", "achieved": achieved, "peak": peak,
-                     "unit": "TFLOP/s", "frac": (achieved / peak) if peak else None, "traffic": traffic,
+                     "unit": "TFLOP/s", "frac": (achieved / peak) if peak else None,
+                     "frac_of_nominal": achieved / nominal, "nominal_peak": nominal, "traffic": traffic,
                      "traffic_note": (f"dram read + write bytes per launch from {traffic_src} (ncu --set full); the kernel is "
                                       "FP32-bound, its algorithmic DRAM traffic is the two 24.9 MB layers it writes") if traffic else None,
                      "algorithmic": f"{FLOP_PER_STEP} flop/RK4 step x {total_steps} steps (SURVEY.md 8d)",
                      "peak_source": "scalar FFMA microbenchmark measured in this run (bhr_measure_fp32_peak); "
-                                    "MEASURED_PEAKS.json holds no FP32 figure"},
+                                    "MEASURED_PEAKS.json holds no FP32 figure; nominal = 148 SM x 128 lanes x 2 x 1.965 GHz"},
         "clocks": clocks,
-        "orbit_video": orbit,
     }
+    if orbit:
+        line["orbit_video_full"] = orbit
     if other:
         line["other_configs"] = other
+    if tiled:
+        line["tiled_4k"] = tiled
     if not args.no_cpu_baseline and world == 1:      # CPU baseline: rank 0 at N = 1 only
-        sys.path.insert(0, os.path.join(ROOT, "tests"))
         tex = r.disk_texture_field.to_numpy()
         times = []
         for _ in range(3):
@@ -421,8 +646,12 @@ def main():
                                 "sample": "3 full frames of the same workload (best of the last 2) with the "
                                           "OpenMP oracle port on all host threads; Taichi is not installable"}
     print(json.dumps(line))
+    sys.stdout.flush()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+    if not tiled_ok:
+        raise SystemExit("tiled_4k: a row-tiled frame differs from the one-GPU frame beyond the flare-sum rounding")
 
 
 if __name__ == "__main__":

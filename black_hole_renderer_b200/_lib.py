@@ -10,9 +10,11 @@ BHR_SKIP_DIFFERENTIALS = 1
 BHR_SKIP_BLOOM = 2
 BHR_WANT_AUX = 4
 SKIP_FLARE = BHR_SKIP_FLARE = 8
+FIELD_COMPOSITE = BHR_FIELD_COMPOSITE = 16
+FLARE_FROM_DEVICE = BHR_FLARE_FROM_DEVICE = 32
 
 (BUF_BG, BUF_DISK, BUF_HBLUR, BUF_FINAL, BUF_FINAL_U8, BUF_CLASS, BUF_STEPS, BUF_DISK_TEX,
- BUF_DISK_MIPS, BUF_COMP, BUF_BLUR) = range(11)
+ BUF_DISK_MIPS, BUF_COMP, BUF_BLUR, BUF_DISK_POST, BUF_FLARE_SUMS) = range(13)
 
 
 class BhrConfig(C.Structure):
@@ -55,6 +57,7 @@ SIGNATURES = {
     "bhr_upload_skybox": (C.c_int, [_P, _FP, C.c_int, C.c_int]),
     "bhr_upload_disk_texture": (C.c_int, [_P, _FP, C.c_int, C.c_int]),
     "bhr_render": (C.c_int, [_P, C.POINTER(BhrCamera), C.c_uint32, _P, _P]),
+    "bhr_device_pci_bus_id": (C.c_int, [C.c_int, C.c_char_p, C.c_int]),
     "bhr_host_register": (C.c_int, [_P, C.c_size_t]),
     "bhr_host_unregister": (C.c_int, [_P]),
     "bhr_peer_export": (C.c_int, [_P, _P]),
@@ -62,15 +65,19 @@ SIGNATURES = {
     "bhr_render_tiled_peer": (C.c_int, [_P, C.POINTER(BhrCamera), C.c_uint32, _P, _P]),
     "bhr_peer_detach": (C.c_int, [_P]),
     "bhr_peer_set_distributed_egress": (C.c_int, [_P, C.c_int]),
+    "bhr_peer_set_tiles": (C.c_int, [_P, C.POINTER(C.c_int)]),
+    "bhr_row_costs": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_uint64)]),
     "bhr_render_async": (C.c_int, [_P, C.POINTER(BhrCamera), C.c_uint32, _P, _P, C.c_int]),
     "bhr_wait_frame": (C.c_int, [_P, C.c_int]),
     "bhr_render_rows_stage1": (C.c_int, [_P, C.POINTER(BhrCamera), C.c_uint32, C.c_int, C.c_int]),
     "bhr_render_rows_stage2": (C.c_int, [_P, C.c_uint32, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "bhr_flare_sums": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_double)]),
+    "bhr_flare_sums_device": (C.c_int, [_P, C.c_int, C.c_int]),
     "bhr_bloom_radius": (C.c_int, [_P]),
     "bhr_buffer": (C.c_int, [_P, C.c_int, C.POINTER(_P), C.POINTER(C.c_size_t)]),
     "bhr_download": (C.c_int, [_P, C.c_int, _P, C.c_size_t]),
     "bhr_last_total_steps": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
+    "bhr_launch_count": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     "bhr_last_retrace_count": (C.c_int, [_P, C.POINTER(C.c_uint32)]),
     "bhr_last_stage_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "bhr_init_background": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_float, _FP, _FP]),

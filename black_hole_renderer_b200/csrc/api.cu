@@ -48,6 +48,7 @@ extern "C" int bhr_create(const bhr_config* cfg, bhr_ctx** out) {
     if (!ctx) return BHR_ERR_NOMEM;
     ctx->cfg = *cfg;
     ctx->W = cfg->width; ctx->H = cfg->height;
+    BhrDeviceGuard device_guard_(cfg->device);          // (the caller's current device is restored on return)
     CREATE_CHECK(cudaSetDevice(cfg->device));
     CREATE_CHECK(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
     ctx->stream = ctx->own_stream;
@@ -61,6 +62,8 @@ extern "C" int bhr_create(const bhr_config* cfg, bhr_ctx** out) {
     CREATE_CHECK(cudaMalloc(&ctx->cls, plane));
     CREATE_CHECK(cudaMalloc(&ctx->steps, plane * sizeof(int)));
     CREATE_CHECK(cudaMalloc(&ctx->d_flare_sums, 3 * sizeof(double)));
+    CREATE_CHECK(cudaMalloc(&ctx->d_flare_parts, BHR_FLARE_BLOCKS * 3 * sizeof(double)));
+    CREATE_CHECK(cudaMalloc(&ctx->d_flare_params_own, bhr_flare_params_size()));
     // [0, plane) u64 re-trace entries of the safety net; then plane i32 band pixels
     CREATE_CHECK(cudaMalloc(&ctx->retrace_queue, plane * (sizeof(unsigned long long) + sizeof(int))));
     CREATE_CHECK(cudaMemset(ctx->retrace_queue, 0, plane * (sizeof(unsigned long long) + sizeof(int))));
@@ -99,13 +102,13 @@ extern "C" int bhr_create(const bhr_config* cfg, bhr_ctx** out) {
 }
 
 extern "C" void bhr_destroy(bhr_ctx* ctx) {
+    BhrDeviceGuard device_guard_(ctx);
     if (!ctx) return;
-    cudaSetDevice(ctx->cfg.device);
     bhr_peer_detach(ctx);
     if (ctx->peer_sync_own) cudaFree(ctx->peer_sync_own);
     if (ctx->own_stream) { cudaStreamSynchronize(ctx->own_stream); }
     void* ptrs[] = {ctx->sky, ctx->mips, ctx->tex_staging, ctx->bg, ctx->disk, ctx->hblur, ctx->blur, ctx->final_f32,
-                    ctx->final_u8, ctx->cls, ctx->steps, ctx->d_flare_sums, ctx->retrace_queue, ctx->d_queue_count, ctx->d_wtab, ctx->d_wsum_x,
+                    ctx->final_u8, ctx->cls, ctx->steps, ctx->d_flare_sums, ctx->d_flare_parts, ctx->d_flare_params_own, ctx->retrace_queue, ctx->d_queue_count, ctx->d_wtab, ctx->d_wsum_x,
                     ctx->d_wsum_y, ctx->comp, ctx->edge, ctx->omega_rows, ctx->row_stats, ctx->d_entities, ctx->stats_scratch, ctx->stats_state, ctx->d_coltab};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int k = 0; k < 6; ++k) if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
@@ -129,6 +132,7 @@ extern "C" int bhr_set_stream(bhr_ctx* ctx, void* cuda_stream) {
 }
 
 extern "C" int bhr_synchronize(bhr_ctx* ctx) {
+    BhrDeviceGuard device_guard_(ctx);
     if (!ctx) return BHR_ERR_INVALID;
     BHR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (ctx->copy_stream) BHR_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
@@ -156,6 +160,7 @@ extern "C" int bhr_set_option(bhr_ctx* ctx, const char* key, double value) {
     if (ctx && !strcmp(key, "stage_timing")) { ctx->stage_timing = (int)value != 0; return BHR_OK; }
     if (ctx && !strcmp(key, "band_box")) { ctx->band_box = (int)value; return BHR_OK; }
     if (ctx && !strcmp(key, "strict_warps")) { ctx->strict_warps = (int)value; return BHR_OK; }
+    if (ctx && !strcmp(key, "peer_timeout_ms")) { ctx->peer_timeout_ms = value; return BHR_OK; }
     if (ctx) snprintf(ctx->err, sizeof(ctx->err), "unknown option %s", key);
     return BHR_ERR_INVALID;
 }
@@ -168,10 +173,10 @@ static int check_rows(bhr_ctx* ctx, int row0, int row1) {
 }
 
 extern "C" int bhr_render_rows_stage1(bhr_ctx* ctx, const bhr_camera* cam, uint32_t flags, int row0, int row1) {
+    BhrDeviceGuard device_guard_(ctx);
     if (!ctx || !cam) return BHR_ERR_INVALID;
     int rc = check_rows(ctx, row0, row1);
     if (rc) return rc;
-    BHR_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
     if (ctx->stage_timing) BHR_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
     rc = bhr_launch_raymarch(ctx, cam, flags, row0, row1);
     if (rc) return rc;
@@ -185,6 +190,7 @@ extern "C" int bhr_render_rows_stage1(bhr_ctx* ctx, const bhr_camera* cam, uint3
 }
 
 extern "C" int bhr_flare_sums(bhr_ctx* ctx, int row0, int row1, double out[3]) {
+    BhrDeviceGuard device_guard_(ctx);
     if (!ctx || !out) return BHR_ERR_INVALID;
     int rc = check_rows(ctx, row0, row1);
     if (rc) return rc;
@@ -195,7 +201,16 @@ extern "C" int bhr_flare_sums(bhr_ctx* ctx, int row0, int row1, double out[3]) {
     return BHR_OK;
 }
 
+extern "C" int bhr_flare_sums_device(bhr_ctx* ctx, int row0, int row1) {
+    BhrDeviceGuard device_guard_(ctx);
+    if (!ctx) return BHR_ERR_INVALID;
+    int rc = check_rows(ctx, row0, row1);
+    if (rc) return rc;
+    return bhr_launch_flare_sums(ctx, row0, row1);
+}
+
 extern "C" int bhr_render_rows_stage2(bhr_ctx* ctx, uint32_t flags, int row0, int row1, const double* flare_sums) {
+    BhrDeviceGuard device_guard_(ctx);
     if (!ctx) return BHR_ERR_INVALID;
     int rc = check_rows(ctx, row0, row1);
     if (rc) return rc;
@@ -214,15 +229,14 @@ static int render_enqueue(bhr_ctx* ctx, const bhr_camera* cam, uint32_t flags, f
                           cudaStream_t copy_stream) {
     int rc = bhr_render_rows_stage1(ctx, cam, flags, 0, ctx->H);
     if (rc) return rc;
-    double sums[3];
-    const double* psums = nullptr;
     if (ctx->cfg.lens_flare && !(flags & BHR_SKIP_FLARE)) {
-        // the flare needs the global brightness centroid before any pixel can be finished
-        rc = bhr_flare_sums(ctx, 0, ctx->H, sums);
+        // the flare needs the global brightness centroid before any pixel can be finished: the three
+        // sums and the parameters derived from them stay on the device (no host round trip)
+        rc = bhr_launch_flare_sums(ctx, 0, ctx->H);
         if (rc) return rc;
-        psums = sums;
+        flags |= BHR_FLARE_FROM_DEVICE;
     }
-    rc = bhr_render_rows_stage2(ctx, flags, 0, ctx->H, psums);
+    rc = bhr_render_rows_stage2(ctx, flags, 0, ctx->H, nullptr);
     if (rc) return rc;
     cudaStream_t cs = ctx->stream;
     if (copy_stream && (out_f32 || out_u8)) {
@@ -374,12 +388,14 @@ static int render_sync_banded(bhr_ctx* ctx, const bhr_camera* cam, uint32_t flag
 }
 
 extern "C" int bhr_render(bhr_ctx* ctx, const bhr_camera* cam, uint32_t flags, float* out_f32, uint8_t* out_u8) {
+    BhrDeviceGuard device_guard_(ctx);
     if (!ctx || !cam) return BHR_ERR_INVALID;
     if (out_f32 || out_u8) return render_sync_banded(ctx, cam, flags, out_f32, out_u8);
     return render_enqueue(ctx, cam, flags, nullptr, nullptr, nullptr);
 }
 
 extern "C" int bhr_render_async(bhr_ctx* ctx, const bhr_camera* cam, uint32_t flags, float* out_f32, uint8_t* out_u8, int slot) {
+    BhrDeviceGuard device_guard_(ctx);
     if (!ctx || !cam || slot < 0 || slot >= 8) return BHR_ERR_INVALID;
     if (!ctx->copy_stream) BHR_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     int rc = render_enqueue(ctx, cam, flags, out_f32, out_u8, ctx->copy_stream);
@@ -390,6 +406,7 @@ extern "C" int bhr_render_async(bhr_ctx* ctx, const bhr_camera* cam, uint32_t fl
 }
 
 extern "C" int bhr_wait_frame(bhr_ctx* ctx, int slot) {
+    BhrDeviceGuard device_guard_(ctx);
     if (!ctx || slot < 0 || slot >= 8) return BHR_ERR_INVALID;
     if (!ctx->frame_ev[slot]) BHR_FAIL(ctx, BHR_ERR_STATE, "no frame was enqueued in slot %d", slot);
     BHR_CUDA(ctx, cudaEventSynchronize(ctx->frame_ev[slot]));
@@ -397,6 +414,7 @@ extern "C" int bhr_wait_frame(bhr_ctx* ctx, int slot) {
 }
 
 extern "C" int bhr_buffer(bhr_ctx* ctx, int id, void** dev_ptr, size_t* bytes) {
+    BhrDeviceGuard device_guard_(ctx);
     if (!ctx || !dev_ptr || !bytes) return BHR_ERR_INVALID;
     const size_t plane = (size_t)ctx->W * ctx->H;
     const size_t tex = (size_t)ctx->n_r * ctx->n_phi;
@@ -412,6 +430,7 @@ extern "C" int bhr_buffer(bhr_ctx* ctx, int id, void** dev_ptr, size_t* bytes) {
         case BHR_BUF_DISK_TEX: *dev_ptr = ctx->mips; *bytes = tex * 16; break;
         case BHR_BUF_DISK_MIPS: *dev_ptr = ctx->mips; *bytes = (size_t)ctx->level_off[BHR_NUM_MIPS] * 16; break;
         case BHR_BUF_COMP: *dev_ptr = ctx->comp; *bytes = ctx->comp ? tex * BHR_N_COMP * 4 : 0; break;
+        case BHR_BUF_FLARE_SUMS: *dev_ptr = ctx->d_flare_sums; *bytes = 3 * sizeof(double); break;
         default: BHR_FAIL(ctx, BHR_ERR_INVALID, "unknown buffer id %d", id);
     }
     if (!*dev_ptr) BHR_FAIL(ctx, BHR_ERR_STATE, "buffer %d not allocated yet", id);
@@ -419,8 +438,23 @@ extern "C" int bhr_buffer(bhr_ctx* ctx, int id, void** dev_ptr, size_t* bytes) {
 }
 
 extern "C" int bhr_download(bhr_ctx* ctx, int id, void* host, size_t bytes) {
+    BhrDeviceGuard device_guard_(ctx);
     if (!ctx || !host) return BHR_ERR_INVALID;
     void* d; size_t n;
+    if (id == BHR_BUF_DISK_POST) {
+        // formed on demand (an inspection path: the reference's disk_layer_field after a bloomed frame)
+        n = (size_t)ctx->W * ctx->H * 12;
+        if (bytes > n) BHR_FAIL(ctx, BHR_ERR_INVALID, "buffer %d holds %zu bytes, %zu requested", id, n, bytes);
+        float* tmp = nullptr;
+        BHR_CUDA(ctx, cudaMalloc(&tmp, n));
+        int rc = bhr_launch_disk_post(ctx, tmp);
+        cudaError_t e = rc ? cudaSuccess : cudaMemcpyAsync(host, tmp, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        cudaFree(tmp);
+        if (rc) return rc;
+        BHR_CUDA(ctx, e);
+        return BHR_OK;
+    }
     int rc = bhr_buffer(ctx, id, &d, &n);
     if (rc) return rc;
     if (bytes > n) BHR_FAIL(ctx, BHR_ERR_INVALID, "buffer %d holds %zu bytes, %zu requested", id, n, bytes);
@@ -429,7 +463,50 @@ extern "C" int bhr_download(bhr_ctx* ctx, int id, void* host, size_t bytes) {
     return BHR_OK;
 }
 
+namespace {
+// RK4 evaluations per image row (the cost model of the row tiles): block per row
+__global__ void __launch_bounds__(256) row_cost_kernel(const int* __restrict__ steps, int W, int row0,
+                                                       unsigned long long* __restrict__ out) {
+    const int* row = steps + (size_t)(row0 + blockIdx.x) * W;
+    unsigned long long s = 0;
+    for (int x = threadIdx.x; x < W; x += 256) s += (unsigned long long)row[x];
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
+    __shared__ unsigned long long sh[8];
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int w = 0; w < 8; ++w) t += sh[w];
+        out[blockIdx.x] = t;
+    }
+}
+}  // namespace
+
+extern "C" int bhr_row_costs(bhr_ctx* ctx, int row0, int row1, uint64_t* out) {
+    BhrDeviceGuard device_guard_(ctx);
+    if (!ctx || !out) return BHR_ERR_INVALID;
+    int rc = check_rows(ctx, row0, row1);
+    if (rc) return rc;
+    if (row1 == row0) return BHR_OK;
+    unsigned long long* d = nullptr;
+    BHR_CUDA(ctx, cudaMalloc(&d, (size_t)(row1 - row0) * sizeof(unsigned long long)));
+    row_cost_kernel<<<row1 - row0, 256, 0, ctx->stream>>>(ctx->steps, ctx->W, row0, d);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d, (size_t)(row1 - row0) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    BHR_CUDA(ctx, e);
+    return BHR_OK;
+}
+
+extern "C" int bhr_launch_count(bhr_ctx* ctx, uint64_t* out) {
+    if (!ctx || !out) return BHR_ERR_INVALID;
+    *out = ctx->launches;
+    return BHR_OK;
+}
+
 extern "C" int bhr_last_total_steps(bhr_ctx* ctx, uint64_t* out) {
+    BhrDeviceGuard device_guard_(ctx);
     if (!ctx || !out) return BHR_ERR_INVALID;
     unsigned long long v = 0;
     BHR_CUDA(ctx, cudaMemcpyAsync(&v, ctx->d_total_steps, sizeof(v), cudaMemcpyDeviceToHost, ctx->stream));
@@ -439,6 +516,7 @@ extern "C" int bhr_last_total_steps(bhr_ctx* ctx, uint64_t* out) {
 }
 
 extern "C" int bhr_last_retrace_count(bhr_ctx* ctx, uint32_t* out) {
+    BhrDeviceGuard device_guard_(ctx);
     if (!ctx || !out) return BHR_ERR_INVALID;
     unsigned int v[2] = {0, 0};
     BHR_CUDA(ctx, cudaMemcpyAsync(v, ctx->d_queue_count, sizeof(v), cudaMemcpyDeviceToHost, ctx->stream));
@@ -448,6 +526,7 @@ extern "C" int bhr_last_retrace_count(bhr_ctx* ctx, uint32_t* out) {
 }
 
 extern "C" int bhr_last_stage_ms(bhr_ctx* ctx, float out[5]) {
+    BhrDeviceGuard device_guard_(ctx);
     if (!ctx || !out) return BHR_ERR_INVALID;
     if (!ctx->ev_valid) BHR_FAIL(ctx, BHR_ERR_STATE, "no frame rendered with stage timing on (option \"stage_timing\")");
     BHR_CUDA(ctx, cudaEventSynchronize(ctx->ev[4]));
@@ -457,6 +536,11 @@ extern "C" int bhr_last_stage_ms(bhr_ctx* ctx, float out[5]) {
     BHR_CUDA(ctx, cudaEventElapsedTime(&out[3], ctx->ev[2], ctx->ev[3]));   // flare reduction / halo gap
     BHR_CUDA(ctx, cudaEventElapsedTime(&out[4], ctx->ev[0], ctx->ev[4]));   // total
     return BHR_OK;
+}
+
+extern "C" int bhr_device_pci_bus_id(int device, char* out, int len) {
+    if (!out || len < 16) return BHR_ERR_INVALID;
+    return cudaDeviceGetPCIBusId(out, len, device) == cudaSuccess ? BHR_OK : BHR_ERR_CUDA;
 }
 
 // pinned host memory for zero-staging D2H of frames
@@ -498,6 +582,7 @@ template <int MODE> __global__ void __launch_bounds__(256) fma_probe(float* out,
 
 extern "C" int bhr_measure_fp32_peak(int device, int mode, double* tflops) {
     if (!tflops) return BHR_ERR_INVALID;
+    BhrDeviceGuard device_guard_(device);
     if (cudaSetDevice(device) != cudaSuccess) return BHR_ERR_CUDA;
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);

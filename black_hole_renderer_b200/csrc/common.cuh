@@ -8,6 +8,7 @@
 #include "../../include/bhr.h"
 
 #define BHR_NUM_MIPS 5          // base + 4 levels, render.py:2239
+#define BHR_FLARE_BLOCKS 592     // blocks of the flare-sum reduction (4 per SM)
 #define BHR_N_COMP 13           // component planes, render.py:2328-2332
 
 // Per-frame parameters of the ray-march kernel (kernel argument, lives in constant bank 0).
@@ -74,6 +75,8 @@ struct bhr_ctx {
     unsigned long long* d_total_steps;
     unsigned long long* retrace_queue; unsigned int* d_queue_count; int retrace_min_cross; unsigned int queue_serial; float retrace_band; int persistent, num_sms, pblock_big, band_lo_auto;
     double* d_flare_sums;              // {sum B, sum x*B, sum y*B}
+    double* d_flare_parts;             // per-block partial sums (BHR_FLARE_BLOCKS x 3)
+    void* d_flare_params_own;          // device FlareParams formed from d_flare_sums (post.cu)
 
     int bloom_R; float sigma_scale;
     float* d_wtab;                     // 3 x wtab_stride (2R+1 weights + zero padding)
@@ -99,11 +102,16 @@ struct bhr_ctx {
     PeerSync* peer_sync_own; PeerSync* peer_sync[16]; PeerSync** d_peer_sync;
     float* peer_hblur[16]; float* peer_final_f32[16]; uint8_t* peer_final_u8[16];
     const float** d_row_src; void* d_flare_params;
+    int peer_bounds[17];               // rank r renders rows [peer_bounds[r], peer_bounds[r + 1])
+    void* peer_rows_host;              // pinned staging of the row-source table
+    int* peer_host_err;                // host-mapped word a wait kernel writes when it gives up (peer.cu)
+    double peer_timeout_ms;
     cudaEvent_t copy_done; int copy_pending;
     // synchronous frames finished in row bands (api.cu): pieces per side of the photon-ring band (0 = off),
     // completion event per band, and "this launch continues a frame: keep the RK4 step total"
     int sync_bands; double sync_min_bytes, sync_extend; cudaEvent_t band_ev[12]; int keep_step_total;
-    int strict_warps, band_box, planar;
+    int strict_warps, band_box, planar, planar_attr_set;
+    unsigned long long launches;       // kernels this context has launched (bhr_launch_count)
     int stage_timing;                  // record the per-stage timing events (instrumentation; each costs ~1.5 us of stream time)
     cudaEvent_t frame_done;            // orders the copy stream behind the composite (no timing)
     int ev_valid;
@@ -128,6 +136,21 @@ extern char g_bhr_create_error[512];
         return (code);                                             \
     } while (0)
 
+// Every entry point that touches the device runs with the context's GPU current and restores the
+// caller's device afterwards: a process may hold contexts on several GPUs, and hosts such as torch
+// switch the current device between calls.
+struct BhrDeviceGuard {
+    int prev = -1, dev = -1;
+    explicit BhrDeviceGuard(int device) : dev(device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (dev >= 0 && prev != dev) cudaSetDevice(dev);
+    }
+    explicit BhrDeviceGuard(const bhr_ctx* ctx) : BhrDeviceGuard(ctx ? ctx->cfg.device : -2) {}
+    ~BhrDeviceGuard() { if (prev >= 0 && prev != dev && dev >= 0) cudaSetDevice(prev); }
+    BhrDeviceGuard(const BhrDeviceGuard&) = delete;
+    BhrDeviceGuard& operator=(const BhrDeviceGuard&) = delete;
+};
+
 static inline int bhr_div_up(int a, int b) { return (a + b - 1) / b; }
 
 // row-tiled frame over several GPUs through peer memory (peer.cu): what the V pass / composite need
@@ -147,5 +170,6 @@ int bhr_launch_bloom_v_composite_ex(bhr_ctx* ctx, uint32_t flags, int row0, int 
 int bhr_launch_flare_params(bhr_ctx* ctx, const double* d_parts, int world, void* d_flare_params);
 size_t bhr_flare_params_size();
 int bhr_launch_flare_sums(bhr_ctx* ctx, int row0, int row1);
+int bhr_launch_disk_post(bhr_ctx* ctx, float* out);
 int bhr_launch_build_mips(bhr_ctx* ctx, int numpy_order);
 int bhr_setup_bloom_tables(bhr_ctx* ctx);

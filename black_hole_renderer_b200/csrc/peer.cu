@@ -23,9 +23,15 @@ struct PeerSync {
     unsigned h_ready[16];        // [r] = s: rank r's H pass (and flare sums) of frame s are complete
     unsigned tile_done[16];      // [r] = s: rank r's rows of frame s are stored in rank 0's final buffers
     unsigned consumed;           // = s: rank 0 has copied frame s out of its final buffers
-    unsigned pad[31];
+    unsigned poison;             // = s: some rank failed while frame s was in flight; waits for frames <= s give up
+    unsigned pad[30];
     double flare_part[16][3];
 };
+// A wait never spins for ever: if a flag does not arrive within the budget (a rank died, raised, or
+// the ranks called an unequal number of times) or the frame is poisoned, the waiting thread stores
+// a code into a host-mapped error word and lets its stream run on (the frame it produces is then
+// garbage); the host finds the code at its next synchronisation / call and returns BHR_ERR_STATE.
+enum : int { PEER_ERR_TIMEOUT = 1, PEER_ERR_POISONED = 2 };
 
 namespace {
 
@@ -51,17 +57,40 @@ __global__ void peer_publish_kernel(PeerSync* const* __restrict__ peers, int ran
     } else if (field == 1) {
         __threadfence_system();
         st_release_sys(&p->tile_done[rank], serial);
-    } else {
+    } else if (field == 2) {
         __threadfence_system();
         st_release_sys(&p->consumed, serial);
+    } else {
+        // poison frame `serial`: this rank cannot finish it.  Its flags are published as well so that
+        // nobody waits for it on this frame.
+        st_release_sys(&p->poison, serial);
+        st_release_sys(&p->h_ready[rank], serial);
+        st_release_sys(&p->tile_done[rank], serial);
+        if (rank == 0) st_release_sys(&p->consumed, serial);
     }
 }
 
-// thread i waits until flags[i] >= serial (flags are in this GPU's own memory)
-__global__ void peer_wait_kernel(const unsigned* __restrict__ flags, int n, unsigned serial) {
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// thread i waits until flags[i] >= serial (flags are in this GPU's own memory), the frame is
+// poisoned, or the budget runs out
+__global__ void peer_wait_kernel(const unsigned* __restrict__ flags, int n, unsigned serial,
+                                 const unsigned* __restrict__ poison, unsigned long long budget_ns,
+                                 volatile int* __restrict__ host_err) {
     const int i = threadIdx.x;
     if (i < n) {
-        while ((int)(ld_acquire_sys(flags + i) - serial) < 0) __nanosleep(200);
+        const unsigned long long t0 = global_ns();
+        while ((int)(ld_acquire_sys(flags + i) - serial) < 0) {
+            if ((int)(ld_acquire_sys(poison) - serial) >= 0) break;
+            if (global_ns() - t0 > budget_ns) { *host_err = PEER_ERR_TIMEOUT; break; }
+            __nanosleep(200);
+        }
+        // (a poisoning rank stores `poison` before its flags, so a wait that its flags released sees it too)
+        if ((int)(ld_acquire_sys(poison) - serial) >= 0 && serial != 0) *host_err = PEER_ERR_POISONED;
     }
     __threadfence_system();
 }
@@ -74,9 +103,27 @@ static void tile_rows(int H, int world, int rank, int* r0, int* r1) {   // == di
     *r1 = *r0 + base + (rank < extra ? 1 : 0);
 }
 
+static int launch_wait(bhr_ctx* ctx, const unsigned* flags, int n, unsigned serial) {
+    const unsigned long long budget = (unsigned long long)(ctx->peer_timeout_ms > 0 ? ctx->peer_timeout_ms : 20000.0) * 1000000ull;
+    peer_wait_kernel<<<1, 32, 0, ctx->stream>>>(flags, n, serial, &ctx->peer_sync_own->poison, budget, ctx->peer_host_err);
+    ++ctx->launches;
+    BHR_CUDA(ctx, cudaGetLastError());
+    return BHR_OK;
+}
+
+// which buffer holds row y of the H-blurred layer, for the current tile bounds (enqueued on the
+// context's stream, i.e. behind the V pass of the previous frame that still reads the old table)
+static int upload_row_sources(bhr_ctx* ctx) {
+    const float** rows = (const float**)ctx->peer_rows_host;
+    for (int r = 0; r < ctx->peer_world; ++r)
+        for (int y = ctx->peer_bounds[r]; y < ctx->peer_bounds[r + 1]; ++y) rows[y] = ctx->peer_hblur[r];
+    BHR_CUDA(ctx, cudaMemcpyAsync(ctx->d_row_src, rows, sizeof(float*) * ctx->H, cudaMemcpyHostToDevice, ctx->stream));
+    return BHR_OK;
+}
+
 extern "C" int bhr_peer_export(bhr_ctx* ctx, bhr_ipc_handle out[4]) {
+    BhrDeviceGuard device_guard_(ctx);
     if (!ctx || !out) return BHR_ERR_INVALID;
-    BHR_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
     if (!ctx->peer_sync_own) {
         BHR_CUDA(ctx, cudaMalloc(&ctx->peer_sync_own, sizeof(PeerSync)));
         BHR_CUDA(ctx, cudaMemset(ctx->peer_sync_own, 0, sizeof(PeerSync)));
@@ -88,10 +135,10 @@ extern "C" int bhr_peer_export(bhr_ctx* ctx, bhr_ipc_handle out[4]) {
 }
 
 extern "C" int bhr_peer_attach(bhr_ctx* ctx, int rank, int world, const bhr_ipc_handle* all) {
+    BhrDeviceGuard device_guard_(ctx);
     if (!ctx || !all || world < 1 || world > 16 || rank < 0 || rank >= world) return BHR_ERR_INVALID;
     if (!ctx->peer_sync_own) BHR_FAIL(ctx, BHR_ERR_STATE, "bhr_peer_export must run first");
     if (ctx->peer_world) BHR_FAIL(ctx, BHR_ERR_STATE, "peers are already attached");
-    BHR_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
     for (int r = 0; r < world; ++r) {
         if (r == rank) {
             ctx->peer_hblur[r] = ctx->hblur; ctx->peer_final_f32[r] = ctx->final_f32;
@@ -104,51 +151,97 @@ extern "C" int bhr_peer_attach(bhr_ctx* ctx, int rank, int world, const bhr_ipc_
         ctx->peer_hblur[r] = (float*)p[0]; ctx->peer_final_f32[r] = (float*)p[1];
         ctx->peer_final_u8[r] = (uint8_t*)p[2]; ctx->peer_sync[r] = (PeerSync*)p[3];
     }
-    // which buffer holds row y of the H-blurred layer
-    const float** rows = (const float**)malloc(sizeof(float*) * ctx->H);
-    if (!rows) BHR_FAIL(ctx, BHR_ERR_NOMEM, "host allocation failed");
+    ctx->peer_rank = rank; ctx->peer_world = world; ctx->peer_serial = 0;
     for (int r = 0; r < world; ++r) {
         int r0, r1;
         tile_rows(ctx->H, world, r, &r0, &r1);
-        for (int y = r0; y < r1; ++y) rows[y] = ctx->peer_hblur[r];
+        ctx->peer_bounds[r] = r0; ctx->peer_bounds[r + 1] = r1;
     }
+    // (pinned: the table upload of bhr_peer_set_tiles must not block behind frames in flight)
+    BHR_CUDA(ctx, cudaMallocHost(&ctx->peer_rows_host, sizeof(float*) * ctx->H));
     BHR_CUDA(ctx, cudaMalloc(&ctx->d_row_src, sizeof(float*) * ctx->H));
-    BHR_CUDA(ctx, cudaMemcpy(ctx->d_row_src, rows, sizeof(float*) * ctx->H, cudaMemcpyHostToDevice));
-    free(rows);
+    {
+        int rc = upload_row_sources(ctx);
+        if (rc) return rc;
+        BHR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    if (!ctx->peer_host_err) {
+        BHR_CUDA(ctx, cudaHostAlloc((void**)&ctx->peer_host_err, sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable));
+        *ctx->peer_host_err = 0;
+    }
     BHR_CUDA(ctx, cudaMalloc(&ctx->d_peer_sync, sizeof(PeerSync*) * 16));
     BHR_CUDA(ctx, cudaMemcpy(ctx->d_peer_sync, ctx->peer_sync, sizeof(PeerSync*) * 16, cudaMemcpyHostToDevice));
     BHR_CUDA(ctx, cudaMalloc(&ctx->d_flare_params, bhr_flare_params_size()));
-    ctx->peer_rank = rank; ctx->peer_world = world; ctx->peer_serial = 0;
+    return BHR_OK;
+}
+
+// Tile boundaries: rank r renders rows [bounds[r], bounds[r + 1]).  Every rank must install the
+// SAME bounds before the same frame (dist.balance_tiles derives them on every rank from all-gathered
+// per-row costs); equal-height tiles until then.
+extern "C" int bhr_peer_set_tiles(bhr_ctx* ctx, const int* bounds) {
+    BhrDeviceGuard device_guard_(ctx);
+    if (!ctx || !bounds) return BHR_ERR_INVALID;
+    if (!ctx->peer_world) BHR_FAIL(ctx, BHR_ERR_STATE, "bhr_peer_attach has not run");
+    if (bounds[0] != 0 || bounds[ctx->peer_world] != ctx->H) BHR_FAIL(ctx, BHR_ERR_INVALID, "tile bounds must run from 0 to the frame height");
+    for (int r = 0; r < ctx->peer_world; ++r)
+        if (bounds[r + 1] < bounds[r]) BHR_FAIL(ctx, BHR_ERR_INVALID, "tile bounds must not decrease");
+    // the pinned staging table may still be read by the previous upload: wait for this stream
+    BHR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int r = 0; r <= ctx->peer_world; ++r) ctx->peer_bounds[r] = bounds[r];
+    return upload_row_sources(ctx);
+}
+
+static int peer_check_error(bhr_ctx* ctx) {
+    const int code = ctx->peer_host_err ? *(volatile int*)ctx->peer_host_err : 0;
+    if (code == PEER_ERR_TIMEOUT) BHR_FAIL(ctx, BHR_ERR_STATE, "peer wait timed out: a rank failed, exited or fell out of step (option \"peer_timeout_ms\")");
+    if (code == PEER_ERR_POISONED) BHR_FAIL(ctx, BHR_ERR_STATE, "a peer rank failed while the frame was in flight");
     return BHR_OK;
 }
 
 static int wait_consumed(bhr_ctx* ctx) {     // before the composite stores into rank 0's final buffers
-    if (ctx->peer_rank != 0) {
-        peer_wait_kernel<<<1, 32, 0, ctx->stream>>>(&ctx->peer_sync_own->consumed, 1, ctx->peer_serial - 1);
-        BHR_CUDA(ctx, cudaGetLastError());
+    if (ctx->peer_rank != 0) return launch_wait(ctx, &ctx->peer_sync_own->consumed, 1, ctx->peer_serial - 1);
+    return BHR_OK;
+}
+
+static int render_tiled_peer_body(bhr_ctx* ctx, const bhr_camera* cam, uint32_t flags, float* out_f32, uint8_t* out_u8, unsigned s);
+
+
+extern "C" int bhr_render_tiled_peer(bhr_ctx* ctx, const bhr_camera* cam, uint32_t flags, float* out_f32, uint8_t* out_u8) {
+    BhrDeviceGuard device_guard_(ctx);
+    if (!ctx || !cam) return BHR_ERR_INVALID;
+    if (!ctx->peer_world) BHR_FAIL(ctx, BHR_ERR_STATE, "bhr_peer_attach has not run");
+    int rc = peer_check_error(ctx);                  // a wait of an earlier frame gave up: the ranks are out of step
+    if (rc) return rc;
+    const unsigned s = ++ctx->peer_serial;
+    rc = render_tiled_peer_body(ctx, cam, flags, out_f32, out_u8, s);
+    if (rc) {
+        // this rank cannot finish frame s: poison it so that every peer's waits drain instead of spinning
+        // (their frame is garbage and they report BHR_ERR_STATE); keep our own error message
+        peer_publish_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_peer_sync, ctx->peer_rank, ctx->peer_world, nullptr, s, 3);
+        ++ctx->launches;
+        cudaStreamSynchronize(ctx->stream);
+        return rc;
     }
     return BHR_OK;
 }
 
-extern "C" int bhr_render_tiled_peer(bhr_ctx* ctx, const bhr_camera* cam, uint32_t flags, float* out_f32, uint8_t* out_u8) {
-    if (!ctx || !cam) return BHR_ERR_INVALID;
-    if (!ctx->peer_world) BHR_FAIL(ctx, BHR_ERR_STATE, "bhr_peer_attach has not run");
-    BHR_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+static int render_tiled_peer_body(bhr_ctx* ctx, const bhr_camera* cam, uint32_t flags, float* out_f32, uint8_t* out_u8, unsigned s) {
     const int rank = ctx->peer_rank, world = ctx->peer_world;
-    const unsigned s = ++ctx->peer_serial;
     PeerSync* mine = ctx->peer_sync_own;
     // distributed egress: every rank copies its own rows into the (shared, page-locked) host frame
     const bool own_egress = rank != 0 && (out_f32 || out_u8);
     const bool host_out = out_f32 || out_u8;
-    int row0, row1;
-    tile_rows(ctx->H, world, rank, &row0, &row1);
+    const int row0 = ctx->peer_bounds[rank], row1 = ctx->peer_bounds[rank + 1];
+    int rc;
     if (rank == 0) {
         // the caller is back for another frame: it is done with frame s - 1 (host frame / final buffers)
         peer_publish_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_peer_sync, rank, world, nullptr, s - 1, 2);
+        ++ctx->launches;
     }
     // every rank has finished frame s - 1 (its V pass no longer reads my H-blurred rows)
-    peer_wait_kernel<<<1, 32, 0, ctx->stream>>>(mine->tile_done, world, s - 1);
-    int rc = bhr_render_rows_stage1(ctx, cam, flags, row0, row1);
+    rc = launch_wait(ctx, mine->tile_done, world, s - 1);
+    if (rc) return rc;
+    rc = bhr_render_rows_stage1(ctx, cam, flags, row0, row1);
     if (rc) return rc;
     const bool flare = ctx->cfg.lens_flare && !(flags & BHR_SKIP_FLARE);
     if (flare) {
@@ -156,7 +249,9 @@ extern "C" int bhr_render_tiled_peer(bhr_ctx* ctx, const bhr_camera* cam, uint32
         if (rc) return rc;
     }
     peer_publish_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_peer_sync, rank, world, flare ? ctx->d_flare_sums : nullptr, s, 0);
-    peer_wait_kernel<<<1, 32, 0, ctx->stream>>>(mine->h_ready, world, s);
+    ++ctx->launches;
+    rc = launch_wait(ctx, mine->h_ready, world, s);
+    if (rc) return rc;
     if (flare) {
         rc = bhr_launch_flare_params(ctx, &mine->flare_part[0][0], world, ctx->d_flare_params);
         if (rc) return rc;
@@ -182,6 +277,7 @@ extern "C" int bhr_render_tiled_peer(bhr_ctx* ctx, const bhr_camera* cam, uint32
                                                   cudaMemcpyDeviceToHost, ctx->stream));
     }
     peer_publish_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_peer_sync, rank, world, nullptr, s, 1);
+    ++ctx->launches;
     BHR_CUDA(ctx, cudaGetLastError());
     if (rank == 0) {
         const bool distributed = host_out && ctx->peer_distributed;
@@ -191,15 +287,20 @@ extern "C" int bhr_render_tiled_peer(bhr_ctx* ctx, const bhr_camera* cam, uint32
                                                        (row1 - row0) * row3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
             if (out_u8) BHR_CUDA(ctx, cudaMemcpyAsync(out_u8 + row0 * row3, ctx->final_u8 + row0 * row3, (row1 - row0) * row3,
                                                       cudaMemcpyDeviceToHost, ctx->stream));
-            peer_wait_kernel<<<1, 32, 0, ctx->stream>>>(mine->tile_done, world, s);
+            rc = launch_wait(ctx, mine->tile_done, world, s);
+            if (rc) return rc;
         } else {
-            peer_wait_kernel<<<1, 32, 0, ctx->stream>>>(mine->tile_done, world, s);
+            rc = launch_wait(ctx, mine->tile_done, world, s);
+            if (rc) return rc;
             const size_t n3 = (size_t)ctx->H * row3;
             if (out_f32) BHR_CUDA(ctx, cudaMemcpyAsync(out_f32, ctx->final_f32, n3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
             if (out_u8) BHR_CUDA(ctx, cudaMemcpyAsync(out_u8, ctx->final_u8, n3, cudaMemcpyDeviceToHost, ctx->stream));
         }
         BHR_CUDA(ctx, cudaGetLastError());
-        if (host_out) BHR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (host_out) {
+            BHR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            return peer_check_error(ctx);
+        }
     }
     return BHR_OK;
 }
@@ -211,9 +312,9 @@ extern "C" int bhr_peer_set_distributed_egress(bhr_ctx* ctx, int enabled) {
 }
 
 extern "C" int bhr_peer_detach(bhr_ctx* ctx) {
+    BhrDeviceGuard device_guard_(ctx);
     if (!ctx) return BHR_ERR_INVALID;
     if (!ctx->peer_world) return BHR_OK;
-    cudaSetDevice(ctx->cfg.device);
     cudaStreamSynchronize(ctx->stream);
     for (int r = 0; r < ctx->peer_world; ++r) {
         if (r == ctx->peer_rank) continue;
@@ -221,7 +322,10 @@ extern "C" int bhr_peer_detach(bhr_ctx* ctx) {
         cudaIpcCloseMemHandle(ctx->peer_final_u8[r]); cudaIpcCloseMemHandle(ctx->peer_sync[r]);
     }
     cudaFree(ctx->d_row_src); cudaFree(ctx->d_peer_sync); cudaFree(ctx->d_flare_params);
+    if (ctx->peer_rows_host) cudaFreeHost(ctx->peer_rows_host);
+    if (ctx->peer_host_err) cudaFreeHost((void*)ctx->peer_host_err);
     ctx->d_row_src = nullptr; ctx->d_peer_sync = nullptr; ctx->d_flare_params = nullptr;
+    ctx->peer_rows_host = nullptr; ctx->peer_host_err = nullptr;
     ctx->peer_world = 0;
     return BHR_OK;
 }

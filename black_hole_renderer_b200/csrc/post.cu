@@ -256,7 +256,8 @@ template <bool BLOOM, int VEC, bool FLARE>
 __global__ void __launch_bounds__(256) composite_kernel(const float* __restrict__ bg, const float* __restrict__ disk,
                                                         const float* __restrict__ blur, float* __restrict__ final_f32,
                                                         uint8_t* __restrict__ final_u8, int W, int row0, int row1,
-                                                        size_t plane, FlareParams F_arg, const FlareParams* __restrict__ F_dev) {
+                                                        size_t plane, FlareParams F_arg, const FlareParams* __restrict__ F_dev,
+                                                        float field_gain) {
     // (peer path: the flare parameters are reduced on the device from every rank's partial sums)
     const FlareParams F = F_dev ? *F_dev : F_arg;
     const int groups_per_row = (W + VEC - 1) / VEC;
@@ -283,7 +284,10 @@ __global__ void __launch_bounds__(256) composite_kernel(const float* __restrict_
             }
 #pragma unroll
             for (int j = 0; j < VEC; ++j) {
-                float t = a[j] + d[j];
+                float dd = d[j];
+                // render_to_field: the disk layer after _bloom_kernel's in-place add (render.py:3112-3114)
+                if (BLOOM && field_gain != 0.0f) dd = fminf(fmaxf(__fadd_rn(dd, __fmul_rn(b[j], field_gain)), 0.0f), 1.0f);
+                float t = a[j] + dd;
                 if (BLOOM) t = t + b[j];
                 v[c][j] = fminf(fmaxf(t, 0.0f), 1.0f);
             }
@@ -344,11 +348,33 @@ __global__ void __launch_bounds__(256) flare_sums_kernel(const float* __restrict
     if (threadIdx.x < 3) {
         double t = 0.0;
         for (int w = 0; w < 8; ++w) t += sh[threadIdx.x][w];
-        atomicAdd(sums + threadIdx.x, t);
+        sums[blockIdx.x * 3 + threadIdx.x] = t;          // per-block partial: summed in block order below (deterministic)
     }
 }
 
+__global__ void flare_sums_final_kernel(const double* __restrict__ parts, int n_blocks, double* __restrict__ sums) {
+    if (threadIdx.x < 3) {
+        double t = 0.0;
+        for (int b = 0; b < n_blocks; ++b) t += parts[b * 3 + threadIdx.x];
+        sums[threadIdx.x] = t;
+    }
+}
+
+// disk_layer_field as _bloom_kernel leaves it: clamp(disk + 0.4 blur, 0, 1), render.py:3112-3114
+__global__ void __launch_bounds__(256) disk_post_kernel(const float* __restrict__ disk, const float* __restrict__ blur,
+                                                        float* __restrict__ out, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = fminf(fmaxf(__fadd_rn(disk[i], __fmul_rn(blur[i], 0.4f)), 0.0f), 1.0f);
+}
+
 }  // namespace
+
+int bhr_launch_disk_post(bhr_ctx* ctx, float* out) {
+    disk_post_kernel<<<148 * 8, 256, 0, ctx->stream>>>(ctx->disk, ctx->blur, out, (size_t)ctx->W * ctx->H * 3);
+    ++ctx->launches;
+    BHR_CUDA(ctx, cudaGetLastError());
+    return BHR_OK;
+}
 
 // weights exp(-d^2 / (sigma2 * sigma_scale)) (render.py:3058-3060) evaluated like the oracle
 // (double exp rounded once), plus the reciprocals of the in-bounds weight sums (summed in the
@@ -401,15 +427,22 @@ int bhr_launch_bloom_h(bhr_ctx* ctx, int row0, int row1) {
     dim3 grid(bhr_div_up(ctx->W, 32 * P_OUT), bhr_div_up(row1 - row0, 8), 3);
     bloom_h_kernel<<<grid, 256, smem, ctx->stream>>>(ctx->disk, ctx->hblur, ctx->W, row0, row1, R, ctx->d_wtab,
                                                      ctx->wtab_stride, ctx->d_wsum_x, (size_t)ctx->W * ctx->H);
+    ++ctx->launches;
     BHR_CUDA(ctx, cudaGetLastError());
     return BHR_OK;
 }
 
+// {sum B, sum x*B, sum y*B} of rows [row0, row1) -> ctx->d_flare_sums (device; stays there unless
+// the caller asks for it).  Per-block partials summed in block order: the same bits on every run.
 int bhr_launch_flare_sums(bhr_ctx* ctx, int row0, int row1) {
-    BHR_CUDA(ctx, cudaMemsetAsync(ctx->d_flare_sums, 0, 3 * sizeof(double), ctx->stream));
-    if (row1 <= row0) return BHR_OK;
-    flare_sums_kernel<<<592, 256, 0, ctx->stream>>>(ctx->disk, ctx->W, row0, row1, (size_t)ctx->W * ctx->H,
-                                                    ctx->d_flare_sums);
+    if (row1 <= row0) {
+        BHR_CUDA(ctx, cudaMemsetAsync(ctx->d_flare_sums, 0, 3 * sizeof(double), ctx->stream));
+        return BHR_OK;
+    }
+    flare_sums_kernel<<<BHR_FLARE_BLOCKS, 256, 0, ctx->stream>>>(ctx->disk, ctx->W, row0, row1, (size_t)ctx->W * ctx->H,
+                                                                 ctx->d_flare_parts);
+    flare_sums_final_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_flare_parts, BHR_FLARE_BLOCKS, ctx->d_flare_sums);
+    ctx->launches += 2;
     BHR_CUDA(ctx, cudaGetLastError());
     return BHR_OK;
 }
@@ -444,6 +477,7 @@ __global__ void flare_params_kernel(const double* __restrict__ parts /* [world][
 
 int bhr_launch_flare_params(bhr_ctx* ctx, const double* d_parts, int world, void* d_flare_params) {
     flare_params_kernel<<<1, 32, 0, ctx->stream>>>(d_parts, world, ctx->W, ctx->H, (FlareParams*)d_flare_params);
+    ++ctx->launches;
     BHR_CUDA(ctx, cudaGetLastError());
     return BHR_OK;
 }
@@ -492,6 +526,7 @@ int bhr_launch_bloom_v_composite_ex(bhr_ctx* ctx, uint32_t flags, int row0, int 
             bloom_v_kernel<false><<<grid, block, smem, ctx->stream>>>(ctx->hblur, ctx->blur, W, H, row0, row1, ctx->bloom_R,
                                                                      ctx->d_wtab, ctx->wtab_stride, ctx->d_wsum_y, plane, nullptr);
         BHR_CUDA(ctx, cudaGetLastError());
+        ++ctx->launches;
     }
     if (ctx->copy_pending) {      // a frame is still being copied out of the final buffers (bhr_render_async)
         BHR_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copy_done, 0));
@@ -504,9 +539,17 @@ int bhr_launch_bloom_v_composite_ex(bhr_ctx* ctx, uint32_t flags, int row0, int 
     float* dst_f32 = peer && peer->final_f32 ? peer->final_f32 : ctx->final_f32;
     uint8_t* dst_u8 = peer && peer->final_u8 ? peer->final_u8 : ctx->final_u8;
     const FlareParams* F_dev = peer ? (const FlareParams*)peer->flare_params : nullptr;
+    if (!peer && (flags & BHR_FLARE_FROM_DEVICE) && !sums) {
+        // the frame-wide sums are in ctx->d_flare_sums (single GPU: just reduced; several GPUs: all-reduced
+        // in place by the caller): form the flare parameters on the device, no host round trip
+        int rc = bhr_launch_flare_params(ctx, ctx->d_flare_sums, 1, ctx->d_flare_params_own);
+        if (rc) return rc;
+        F_dev = (const FlareParams*)ctx->d_flare_params_own;
+    }
     const int cgrid = 148 * 8;
+    const float field_gain = (flags & BHR_FIELD_COMPOSITE) ? 0.4f : 0.0f;
 #define BHR_COMPOSITE(B, V, FL) composite_kernel<B, V, FL><<<cgrid, 256, 0, ctx->stream>>>( \
-        ctx->bg, ctx->disk, ctx->blur, dst_f32, dst_u8, W, row0, row1, plane, F, F_dev)
+        ctx->bg, ctx->disk, ctx->blur, dst_f32, dst_u8, W, row0, row1, plane, F, F_dev, field_gain)
     const bool vec = (W % 4 == 0), fl = F.enabled != 0 || F_dev != nullptr;
     if (vec) {
         if (bloom) { if (fl) BHR_COMPOSITE(true, 4, true); else BHR_COMPOSITE(true, 4, false); }
@@ -516,6 +559,7 @@ int bhr_launch_bloom_v_composite_ex(bhr_ctx* ctx, uint32_t flags, int row0, int 
         else { if (fl) BHR_COMPOSITE(false, 1, true); else BHR_COMPOSITE(false, 1, false); }
     }
 #undef BHR_COMPOSITE
+    ++ctx->launches;
     BHR_CUDA(ctx, cudaGetLastError());
     return BHR_OK;
 }

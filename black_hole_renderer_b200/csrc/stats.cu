@@ -190,6 +190,7 @@ static int ensure_stats_storage(bhr_ctx* ctx) {
 }
 
 extern "C" int bhr_stats_prepare(bhr_ctx* ctx, int enable_rt, uint64_t* n_total, uint64_t* n_positive) {
+    BhrDeviceGuard device_guard_(ctx);
     if (!ctx || !n_total || !n_positive) return BHR_ERR_INVALID;
     if (!ctx->bg_ready) BHR_FAIL(ctx, BHR_ERR_STATE, "Must call init_background_layer() first");
     int rc = ensure_stats_storage(ctx);
@@ -213,6 +214,7 @@ extern "C" int bhr_stats_prepare(bhr_ctx* ctx, int enable_rt, uint64_t* n_total,
 }
 
 extern "C" int bhr_stats_select(bhr_ctx* ctx, uint64_t rank_density, uint64_t rank_struct, float out[4]) {
+    BhrDeviceGuard device_guard_(ctx);
     if (!ctx || !out) return BHR_ERR_INVALID;
     if (!ctx->stats_scratch) BHR_FAIL(ctx, BHR_ERR_STATE, "bhr_stats_prepare has not run");
     const size_t plane = (size_t)ctx->n_r * ctx->n_phi;
@@ -239,6 +241,7 @@ extern "C" int bhr_stats_select(bhr_ctx* ctx, uint64_t rank_density, uint64_t ra
 }
 
 extern "C" int bhr_stats_rows(bhr_ctx* ctx, float denom, int lo, int hi, float* out) {
+    BhrDeviceGuard device_guard_(ctx);
     if (!ctx || !out) return BHR_ERR_INVALID;
     if (!ctx->stats_scratch) BHR_FAIL(ctx, BHR_ERR_STATE, "bhr_stats_prepare has not run");
     if (lo < 0 || hi < lo || hi >= ctx->n_phi) BHR_FAIL(ctx, BHR_ERR_INVALID, "quantile neighbours out of range");

@@ -420,6 +420,7 @@ int bhr_launch_build_mips(bhr_ctx* ctx, int numpy_order) {
         dim3 block(32, 8), grid(bhr_div_up(dw, 32), bhr_div_up(dh, 8));
         mip_down_kernel<<<grid, block, 0, ctx->stream>>>(ctx->mips + ctx->level_off[lev - 1], ctx->mips + ctx->level_off[lev],
                                                          dh, dw, w, numpy_order);
+        ++ctx->launches;
         h = dh; w = dw;
     }
     BHR_CUDA(ctx, cudaGetLastError());
@@ -427,6 +428,7 @@ int bhr_launch_build_mips(bhr_ctx* ctx, int numpy_order) {
 }
 
 extern "C" int bhr_upload_skybox(bhr_ctx* ctx, const float* rgb, int h, int w) {
+    BhrDeviceGuard device_guard_(ctx);
     if (!ctx || !rgb || h <= 0 || w <= 0) return BHR_ERR_INVALID;
     size_t n = (size_t)h * w;
     float* staging = nullptr;
@@ -460,6 +462,7 @@ static int ensure_disk_storage(bhr_ctx* ctx, int n_r, int n_phi) {
 }
 
 extern "C" int bhr_upload_disk_texture(bhr_ctx* ctx, const float* rgba, int n_r, int n_phi) {
+    BhrDeviceGuard device_guard_(ctx);
     if (!ctx || !rgba) return BHR_ERR_INVALID;
     int rc = ensure_disk_storage(ctx, n_r, n_phi);
     if (rc) return rc;
@@ -472,6 +475,7 @@ extern "C" int bhr_upload_disk_texture(bhr_ctx* ctx, const float* rgba, int n_r,
 
 extern "C" int bhr_init_background(bhr_ctx* ctx, int n_r, int n_phi, int az_freq, float az_shear, const float* edge,
                                    const float* omega_rows) {
+    BhrDeviceGuard device_guard_(ctx);
     if (!ctx || !edge || !omega_rows) return BHR_ERR_INVALID;
     int rc = ensure_disk_storage(ctx, n_r, n_phi);
     if (rc) return rc;
@@ -492,6 +496,7 @@ extern "C" int bhr_init_background(bhr_ctx* ctx, int n_r, int n_phi, int az_freq
 }
 
 extern "C" int bhr_generate_background(bhr_ctx* ctx, float t) {
+    BhrDeviceGuard device_guard_(ctx);
     if (!ctx) return BHR_ERR_INVALID;
     if (!ctx->bg_ready) BHR_FAIL(ctx, BHR_ERR_STATE, "Must call init_background_layer() first");
     // one block per (row, column chunk); the block width that wastes the fewest lanes on the ragged
@@ -503,11 +508,13 @@ extern "C" int bhr_generate_background(bhr_ctx* ctx, float t) {
     }
     background_kernel<<<dim3(bhr_div_up(ctx->n_phi, best), ctx->n_r), best, 0, ctx->stream>>>(
         ctx->comp, ctx->n_r, ctx->n_phi, ctx->az_freq, ctx->az_shear, ctx->cfg.r_disk_inner, ctx->cfg.r_disk_outer, t);
+    ++ctx->launches;
     BHR_CUDA(ctx, cudaGetLastError());
     return BHR_OK;
 }
 
 extern "C" int bhr_accumulate_entities(bhr_ctx* ctx, const bhr_entity* entities, int n) {
+    BhrDeviceGuard device_guard_(ctx);
     if (!ctx || (n > 0 && !entities)) return BHR_ERR_INVALID;
     if (!ctx->bg_ready) BHR_FAIL(ctx, BHR_ERR_STATE, "Must call init_background_layer() first");
     // host staging ring (pinned): the caller's array may be reused as soon as we return, and the
@@ -554,6 +561,7 @@ extern "C" int bhr_accumulate_entities(bhr_ctx* ctx, const bhr_entity* entities,
     if (n_tab > 0) {
         dim3 g(bhr_div_up(ctx->n_phi, 256), n_tab);
         entity_coltab_kernel<<<g, 256, 0, ctx->stream>>>(d_ent, d_slot_ent, ctx->n_phi, coltab);
+        ++ctx->launches;
     }
     const size_t smem = (size_t)n * sizeof(RowEntity);
     if (smem > 200 * 1024) BHR_FAIL(ctx, BHR_ERR_INVALID, "too many entities (%d) for the per-row list", n);
@@ -562,12 +570,14 @@ extern "C" int bhr_accumulate_entities(bhr_ctx* ctx, const bhr_entity* entities,
     dim3 grid(bhr_div_up(ctx->n_phi, kEntCols), ctx->n_r);
     entity_accumulate_kernel<<<grid, 256, smem, ctx->stream>>>(ctx->comp, ctx->n_r, ctx->n_phi, d_ent, n, ctx->omega_rows,
                                                                d_slot, coltab);
+    ++ctx->launches;
     BHR_CUDA(ctx, cudaGetLastError());
     BHR_CUDA(ctx, cudaEventRecord(ctx->ent_ev[ring], ctx->stream));
     return BHR_OK;
 }
 
 extern "C" int bhr_set_stats(bhr_ctx* ctx, float density_p98, float struct_scale, const float* row_stats) {
+    BhrDeviceGuard device_guard_(ctx);
     if (!ctx || !row_stats) return BHR_ERR_INVALID;
     if (!ctx->bg_ready) BHR_FAIL(ctx, BHR_ERR_STATE, "Must call init_background_layer() first");
     ctx->stats[0] = density_p98; ctx->stats[1] = struct_scale;
@@ -577,6 +587,7 @@ extern "C" int bhr_set_stats(bhr_ctx* ctx, float density_p98, float struct_scale
 }
 
 extern "C" int bhr_upload_comp(bhr_ctx* ctx, const float* comp) {
+    BhrDeviceGuard device_guard_(ctx);
     if (!ctx || !comp) return BHR_ERR_INVALID;
     if (!ctx->bg_ready) BHR_FAIL(ctx, BHR_ERR_STATE, "Must call init_background_layer() first");
     const size_t bytes = (size_t)ctx->n_r * ctx->n_phi * BHR_N_COMP * sizeof(float);
@@ -586,18 +597,21 @@ extern "C" int bhr_upload_comp(bhr_ctx* ctx, const float* comp) {
 }
 
 extern "C" int bhr_compose_texture(bhr_ctx* ctx, float t_offset, int enable_rt, float color_temp) {
+    BhrDeviceGuard device_guard_(ctx);
     if (!ctx) return BHR_ERR_INVALID;
     if (!ctx->bg_ready) BHR_FAIL(ctx, BHR_ERR_STATE, "Must call init_background_layer() first");
     const size_t plane = (size_t)ctx->n_r * ctx->n_phi;
     compose_kernel<<<(unsigned)((plane + 255) / 256), 256, 0, ctx->stream>>>(
         ctx->comp, ctx->omega_rows, ctx->edge, ctx->stats[0], ctx->stats[1], ctx->row_stats, ctx->n_r, ctx->n_phi,
         t_offset, enable_rt, color_temp, ctx->mips);
+    ++ctx->launches;
     BHR_CUDA(ctx, cudaGetLastError());
     return bhr_launch_build_mips(ctx, 0);
 }
 
 extern "C" int bhr_eval_noise(bhr_ctx* ctx, const float* coords, int n, int mode, int octaves, float persistence,
                               float lacunarity, float* out) {
+    BhrDeviceGuard device_guard_(ctx);
     if (!ctx || !coords || !out || n < 0) return BHR_ERR_INVALID;
     if (n == 0) return BHR_OK;
     float *dc = nullptr, *dout = nullptr;

@@ -24,65 +24,101 @@ def tile_rows(height, world_size, rank):
     return row0, row0 + base + (1 if rank < extra else 0)
 
 
-def owners_of_rows(height, world_size, lo, hi):
+def equal_bounds(height, world_size):
+    """Tile boundaries [b_0 = 0, ..., b_world = height] of the equal-height split."""
+    return [tile_rows(height, world_size, r)[0] for r in range(world_size)] + [height]
+
+
+def balanced_bounds(row_costs, world_size, min_rows=1):
+    """Tile boundaries that give every rank (nearly) the same total cost: b_r is the first row at
+    which the running cost reaches r / world of the total.  `row_costs`: one non-negative number
+    per image row (RK4 evaluations + a per-pixel post-processing term, see `balance_tiles`)."""
+    c = np.asarray(row_costs, dtype=np.float64)
+    H = len(c)
+    cum = np.concatenate([[0.0], np.cumsum(c)])
+    total = cum[-1] if cum[-1] > 0 else 1.0
+    bounds = [0]
+    for r in range(1, world_size):
+        target = total * r / world_size
+        b = int(np.searchsorted(cum, target, side="left"))
+        if 0 < b <= H and abs(cum[b - 1] - target) < abs(cum[min(b, H)] - target):
+            b -= 1                        # the nearer of the two candidate rows
+        b = min(max(b, bounds[-1] + min_rows), H - (world_size - r) * min_rows)
+        bounds.append(b)
+    bounds.append(H)
+    return bounds
+
+
+def owners_of_rows(height, world_size, lo, hi, bounds=None):
     """[(rank, a, b)]: which ranks own the rows [lo, hi) (clipped to the frame)."""
+    bounds = bounds or equal_bounds(height, world_size)
     lo, hi = max(lo, 0), min(hi, height)
     out = []
     for r in range(world_size):
-        r0, r1 = tile_rows(height, world_size, r)
-        a, b = max(lo, r0), min(hi, r1)
+        a, b = max(lo, bounds[r]), min(hi, bounds[r + 1])
         if a < b:
             out.append((r, a, b))
     return out
 
 
-def exchange_halos(plane, height, radius, rank, world_size, group=None):
+def exchange_halos(plane, height, radius, rank, world_size, group=None, bounds=None):
     """Fill rows [row0 - radius, row0) and [row1, row1 + radius) of `plane` (C, H, W) with the
     neighbours' data; every rank sends the rows of its own tile that others need.  Handles tiles
-    shorter than the radius (a halo may span several ranks)."""
+    shorter than the radius (a halo may span several ranks).  Rows of one channel are contiguous,
+    so every transfer goes straight out of / into `plane[c, a:b]` -- one send / recv per channel
+    and neighbour piece, no staging copies."""
     if world_size == 1:
         return
-    row0, row1 = tile_rows(height, world_size, rank)
-    ops, keep = [], []
+    bounds = bounds or equal_bounds(height, world_size)
+    row0, row1 = bounds[rank], bounds[rank + 1]
+    n_ch = plane.shape[0]
+    ops = []
     # what I need from others
     for lo, hi in ((row0 - radius, row0), (row1, row1 + radius)):
-        for r, a, b in owners_of_rows(height, world_size, lo, hi):
+        for r, a, b in owners_of_rows(height, world_size, lo, hi, bounds):
             if r == rank:
                 continue
-            buf = torch.empty_like(plane[:, a:b, :]).contiguous()
-            keep.append((buf, a, b))
-            ops.append(dist.P2POp(dist.irecv, buf, r, group=group))
+            for c in range(n_ch):
+                ops.append(dist.P2POp(dist.irecv, plane[c, a:b], r, group=group))
     # what others need from me
     for r in range(world_size):
         if r == rank:
             continue
-        p0, p1 = tile_rows(height, world_size, r)
+        p0, p1 = bounds[r], bounds[r + 1]
         for lo, hi in ((p0 - radius, p0), (p1, p1 + radius)):
             a, b = max(lo, row0, 0), min(hi, row1, height)
             if a < b:
-                ops.append(dist.P2POp(dist.isend, plane[:, a:b, :].contiguous(), r, group=group))
+                for c in range(n_ch):
+                    ops.append(dist.P2POp(dist.isend, plane[c, a:b], r, group=group))
     if ops:
         for req in dist.batch_isend_irecv(ops):
             req.wait()
-    for buf, a, b in keep:
-        plane[:, a:b, :].copy_(buf)
 
 
-def gather_rows(tile, height, rank, world_size, dst=0, group=None):
-    """Gather the (rows, W, C) tiles on `dst`; returns the (H, W, C) frame there, None elsewhere."""
+def gather_rows(tile, height, rank, world_size, dst=0, group=None, bounds=None, out=None):
+    """Gather the (rows, W, C) tiles on `dst`; returns the (H, W, C) frame there, None elsewhere.
+    `out`: the full (H, W, C) tensor on `dst` whose own rows `tile` aliases -- the other ranks' tiles
+    are then received straight into their rows (no concatenation)."""
     if world_size == 1:
-        return tile
+        return tile if out is None else out
+    bounds = bounds or equal_bounds(height, world_size)
     if rank == dst:
+        if out is not None:
+            reqs = [dist.irecv(out[bounds[r]:bounds[r + 1]], r, group=group) for r in range(world_size)
+                    if r != dst and bounds[r + 1] > bounds[r]]
+            for q in reqs:
+                q.wait()
+            return out
         parts = []
         for r in range(world_size):
-            r0, r1 = tile_rows(height, world_size, r)
-            parts.append(tile if r == dst else torch.empty((r1 - r0,) + tuple(tile.shape[1:]),
+            parts.append(tile if r == dst else torch.empty((bounds[r + 1] - bounds[r],) + tuple(tile.shape[1:]),
                                                            dtype=tile.dtype, device=tile.device))
-        reqs = [dist.irecv(parts[r], r, group=group) for r in range(world_size) if r != dst]
+        reqs = [dist.irecv(parts[r], r, group=group) for r in range(world_size) if r != dst and parts[r].shape[0] > 0]
         for q in reqs:
             q.wait()
         return torch.cat(parts, dim=0)
-    dist.send(tile.contiguous(), dst, group=group)
+    if tile.shape[0] > 0:
+        dist.send(tile.contiguous(), dst, group=group)
     return None
 
 
@@ -93,24 +129,34 @@ class _CudaView:
 
 
 def device_tensor(renderer, buf_id, shape, dtype=torch.float32):
-    """torch tensor aliasing one of the renderer's device buffers (no copy)."""
-    ptr, _ = renderer.device_buffer(buf_id)
-    typestr = {torch.float32: "<f4", torch.uint8: "|u1", torch.int32: "<i4"}[dtype]
-    return torch.as_tensor(_CudaView(ptr, shape, typestr), device=f"cuda:{renderer.cuda_device}")
+    """torch tensor aliasing one of the renderer's device buffers (no copy; cached per buffer)."""
+    cache = renderer.__dict__.setdefault("_device_tensors", {})
+    key = (buf_id, tuple(shape), dtype)
+    t = cache.get(key)
+    if t is None:
+        ptr, _ = renderer.device_buffer(buf_id)
+        typestr = {torch.float32: "<f4", torch.uint8: "|u1", torch.int32: "<i4", torch.float64: "<f8"}[dtype]
+        t = cache[key] = torch.as_tensor(_CudaView(ptr, shape, typestr), device=f"cuda:{renderer.cuda_device}")
+    return t
 
 
 def render_tiled(renderer, cam_pos, fov, frame=0, skip_differentials=False, skip_bloom=False,
-                 rank=0, world_size=1, group=None, want_u8=False, copy=True):
+                 rank=0, world_size=1, group=None, want_u8=False, copy=True, bounds=None):
     """One frame split into row tiles over `world_size` GPUs (render.py:3865-3923 semantics).
 
     stage 1 (ray march + horizontal bloom pass on my rows) -> halo exchange of the H-blurred layer
-    -> all-reduce of the flare sums -> stage 2 (vertical pass + composite + flare on my rows)
-    -> gather on rank 0.  Returns the (H, W, 3) frame (numpy) on rank 0, None elsewhere; with
-    copy=False the array aliases a per-renderer pinned buffer that the next call overwrites.
+    (NCCL send / recv straight out of and into the layer buffer) -> all-reduce of the three flare
+    sums IN PLACE in the device buffer stage 2 reads (no host round trip) -> stage 2 (vertical pass
+    + composite + flare on my rows) -> tiles received straight into rank 0's frame buffer -> one
+    D2H on rank 0.  Returns the (H, W, 3) frame (numpy) on rank 0, None elsewhere; with copy=False
+    the array aliases a per-renderer pinned buffer that the next call overwrites.  After
+    `attach_shared_frame` (u8 frames) every rank copies its own rows into the shared host frame
+    over its own PCIe link instead of the gather.
     """
     import ctypes as C
     H, W = renderer.height, renderer.width
-    row0, row1 = tile_rows(H, world_size, rank)
+    bounds = bounds or equal_bounds(H, world_size)
+    row0, row1 = bounds[rank], bounds[rank + 1]
     lib, ctx = renderer._lib, renderer._ctx
     stream = torch.cuda.current_stream(renderer.cuda_device)
     if stream.cuda_stream == 0:           # legacy default stream: give torch and the kernels a real one
@@ -122,22 +168,32 @@ def render_tiled(renderer, cam_pos, fov, frame=0, skip_differentials=False, skip
     L.check(ctx, lib.bhr_render_rows_stage1(ctx, C.byref(cam), flags, row0, row1))
     if not skip_bloom:
         hblur = device_tensor(renderer, L.BUF_HBLUR, (3, H, W))
-        exchange_halos(hblur, H, renderer._lib.bhr_bloom_radius(ctx), rank, world_size, group)
-    sums_ptr = None
+        exchange_halos(hblur, H, renderer._lib.bhr_bloom_radius(ctx), rank, world_size, group, bounds)
     if renderer.lens_flare:
-        sums = (C.c_double * 3)()
-        L.check(ctx, lib.bhr_flare_sums(ctx, row0, row1, sums))
-        t = torch.tensor(list(sums), dtype=torch.float64, device=f"cuda:{renderer.cuda_device}")
+        L.check(ctx, lib.bhr_flare_sums_device(ctx, row0, row1))
         if world_size > 1:
-            dist.all_reduce(t, group=group)
-        vals = t.cpu().tolist()
-        sums_ptr = (C.c_double * 3)(*vals)
-    L.check(ctx, lib.bhr_render_rows_stage2(ctx, flags, row0, row1, sums_ptr))
+            dist.all_reduce(device_tensor(renderer, L.BUF_FLARE_SUMS, (3,), torch.float64), group=group)
+        flags |= L.FLARE_FROM_DEVICE
+    L.check(ctx, lib.bhr_render_rows_stage2(ctx, flags, row0, row1, None))
+    renderer._disk_post_bloom = not skip_bloom
+    shared = renderer.__dict__.get("_shared_frame")
+    if shared is not None and world_size > 1:
+        # distributed egress: my rows -> the shared, page-locked host frame over my own PCIe link
+        assert want_u8 == (shared.dtype == np.uint8)
+        buf = L.BUF_FINAL_U8 if want_u8 else L.BUF_FINAL
+        full = device_tensor(renderer, buf, (H, W, 3), torch.uint8 if want_u8 else torch.float32)
+        host = renderer.__dict__.get("_shared_frame_t")
+        if host is None:
+            host = renderer._shared_frame_t = torch.from_numpy(shared)
+        host[row0:row1].copy_(full[row0:row1], non_blocking=True)
+        stream.synchronize()
+        dist.barrier(group=group)         # (host-side rendezvous: every rank's rows have landed)
+        return (shared.copy() if copy else shared) if rank == 0 else None
     if want_u8:
         full = device_tensor(renderer, L.BUF_FINAL_U8, (H, W, 3), torch.uint8)
     else:
         full = device_tensor(renderer, L.BUF_FINAL, (H, W, 3))
-    frame_t = gather_rows(full[row0:row1], H, rank, world_size, 0, group)
+    frame_t = gather_rows(full[row0:row1], H, rank, world_size, 0, group, bounds, out=full if rank == 0 else None)
     if frame_t is None:
         return None
     # page-locked landing buffer (cached per renderer and dtype): the D2H copy runs at PCIe speed
@@ -148,6 +204,40 @@ def render_tiled(renderer, cam_pos, fov, frame=0, skip_differentials=False, skip
     host.copy_(frame_t, non_blocking=True)
     torch.cuda.current_stream(renderer.cuda_device).synchronize()
     return host.numpy().copy() if copy else host.numpy()     # copy=False: valid until the next call
+
+
+def balance_tiles(renderer, cam_pos, fov, rank, world_size, group=None, post_cost_per_pixel=10.0,
+                  skip_differentials=False):
+    """Cost-balanced tile boundaries for `render_tiled` / `render_tiled_peer`: rows through the hole
+    and the disk cost more than sky rows.  Every rank traces its equal-height tile once with the
+    per-pixel step counts on, reduces them to RK4 evaluations per row on the device
+    (bhr_row_costs), the per-row costs are all-gathered, and every rank derives the same
+    boundaries (`balanced_bounds`; cost of a row = its RK4 evaluations + `post_cost_per_pixel`
+    step-equivalents per pixel for bloom / composite / egress).  For a camera path the boundaries
+    of one frame serve its neighbours (the cost profile moves slowly).  Returns the bounds list;
+    with peers attached it is installed in the library as well."""
+    import ctypes as C
+    H, W = renderer.height, renderer.width
+    eq = equal_bounds(H, world_size)
+    row0, row1 = eq[rank], eq[rank + 1]
+    lib, ctx = renderer._lib, renderer._ctx
+    cam = renderer._camera(cam_pos, fov, 0)
+    flags = renderer._flags(skip_differentials, True, aux=True)
+    L.check(ctx, lib.bhr_render_rows_stage1(ctx, C.byref(cam), flags, row0, row1))
+    costs = np.zeros(row1 - row0, dtype=np.uint64)
+    L.check(ctx, lib.bhr_row_costs(ctx, row0, row1, costs.ctypes.data_as(C.POINTER(C.c_uint64))))
+    everyone = [None] * world_size
+    if world_size > 1:
+        dist.all_gather_object(everyone, costs.tolist(), group=group)
+    else:
+        everyone = [costs.tolist()]
+    rows = np.concatenate([np.asarray(e, dtype=np.float64) for e in everyone]) + post_cost_per_pixel * W
+    bounds = balanced_bounds(rows, world_size, min_rows=8)
+    if renderer.__dict__.get("_peer_world"):
+        arr = (C.c_int * (world_size + 1))(*bounds)
+        L.check(ctx, lib.bhr_peer_set_tiles(ctx, arr))
+    renderer._tile_bounds = bounds
+    return bounds
 
 
 # ----------------------------------------------------------------------------------------------

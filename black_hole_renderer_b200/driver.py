@@ -128,6 +128,96 @@ def frame_owner(frame, world_size, block=STATS_PERIOD):
     return (frame // block) % world_size
 
 
+def load_progress(temp_dir, params):
+    """Completed frames recorded under `temp_dir`: the union of progress.json (a finished or
+    single-process run) and every progress.<rank>.json (what the ranks of an interrupted sharded
+    run left behind).  Returns (completed set, params_match): a file written with other parameters
+    invalidates the whole directory, like the reference's check (render.py:4392-4405)."""
+    completed, match = set(), True
+    if not os.path.isdir(temp_dir):
+        return completed, match
+    for name in sorted(os.listdir(temp_dir)):
+        if not (name == "progress.json" or (name.startswith("progress.") and name.endswith(".json"))):
+            continue
+        try:
+            with open(os.path.join(temp_dir, name)) as f:
+                saved = json.load(f)
+        except (OSError, ValueError):
+            continue                        # a file cut off by the crash: its frames are re-rendered
+        if saved.get("params", {}) != params:
+            match = False
+            continue
+        completed |= {int(f) for f in saved.get("completed", [])
+                      if os.path.isfile(os.path.join(temp_dir, f"frame_{int(f):04d}.png"))}
+    return completed, match
+
+
+def run_video_frames(renderer, n_frames, fov, static_cam_pos, orbit, orbit_degrees, dt, rank=0, world_size=1,
+                     completed=(), sink=None, on_rendered=None, ring=24, depth=5, factories=None):
+    """The frame loop of render_video (render.py:4437-4458) for the frames `rank` owns.
+
+    Pipelined: frames are enqueued without waiting (texture kernels, render, D2H into one of `ring`
+    pinned buffers) and the host runs up to `depth` frames ahead of the device: it does the
+    lifecycle ticks / entity packing of the next frames -- and, with several ranks, the ticks of
+    the frames other ranks own -- while the device works; a frame is retired (waited for, handed to
+    `sink(frame, u8_array)`) when `depth` newer ones are in flight.  `sink` may return a future: the
+    buffer is not reused before it resolves.
+
+    Lifecycle state: every rank ticks the factories of EVERY frame (the RNG streams are the
+    contract); the device stages are stateless functions of (t, factories) except the statistics,
+    which frame 60 b fixes for block b.  A block that still has frames to render therefore starts
+    with the full texture pass + statistics of its first frame even when that frame is already done
+    (resume), so resumed frames equal those of an uninterrupted run.
+    Returns the number of frames rendered."""
+    if factories is None:
+        factories = init_lifecycle_system(renderer, renderer.dtex_h, renderer.dtex_w, seed=42)
+    completed = set(completed)
+    bufs = [renderer.pinned_frame(np.uint8) for _ in range(ring)]
+    busy = [None] * ring                       # future of the sink still reading the buffer
+    in_flight = []                             # (frame, slot) enqueued, not yet waited for
+
+    def retire(item):
+        frame_done, slot = item
+        renderer.wait_frame(slot % 8)          # (eight completion-event slots; depth + 1 <= 8 frames in flight)
+        if sink is not None:
+            busy[slot] = sink(frame_done, bufs[slot])
+
+    def block_has_work(first):
+        return any(f not in completed for f in range(first, min(first + STATS_PERIOD, n_frames)))
+
+    rendered = 0
+    for frame in range(n_frames):
+        t = frame * dt
+        mine = frame_owner(frame, world_size) == rank
+        block_start = frame % STATS_PERIOD == 0
+        if mine and frame not in completed:
+            cam_pos = orbit_camera(static_cam_pos, frame, n_frames, orbit_degrees) if orbit else static_cam_pos
+            slot = rendered % ring
+            if busy[slot] is not None:
+                busy[slot].result()
+                busy[slot] = None
+            advance_lifecycle_frame(renderer, factories, t, dt, recompute_stats=block_start)
+            renderer.render_u8_async(cam_pos, fov, bufs[slot], slot % 8, frame=0)
+            in_flight.append((frame, slot))
+            if len(in_flight) > depth:
+                retire(in_flight.pop(0))
+            rendered += 1
+            if on_rendered is not None:
+                on_rendered(rendered, frame)
+        elif mine and block_start and block_has_work(frame):
+            # resumed block: its first frame is on disk already, but its statistics are needed
+            advance_lifecycle_frame(renderer, factories, t, dt, recompute_stats=True)
+        else:
+            for f in factories.values():      # keep the RNG streams in step; no device work
+                f.tick(now=t, dt=dt)
+    for item in in_flight:
+        retire(item)
+    for b in busy:
+        if b is not None:
+            b.result()
+    return rendered
+
+
 def render_video(renderer, width, height, n_frames, fps, output_path, fov, static_cam_pos,
                  orbit=False, resume=False, disk_rotation_speed=0.1, orbit_degrees=360.0,
                  rank=0, world_size=1, barrier=None, **_deprecated_kwargs):
@@ -135,7 +225,9 @@ def render_video(renderer, width, height, n_frames, fps, output_path, fov, stati
 
     Same temp-dir / progress.json protocol as the reference (render.py:4380-4405, 4469-4472).
     With world_size > 1 each rank renders the frames it owns (`frame_owner`), writes
-    progress.<rank>.json, and rank 0 merges the per-rank lists and muxes after `barrier()`.
+    progress.<rank>.json as it goes, and rank 0 merges the per-rank lists and muxes after
+    `barrier()`.  `--resume` reads the merged file AND the per-rank files of an interrupted run; a
+    frame is listed only once its PNG is on disk.
     """
     out_dir = os.path.dirname(output_path)
     os.makedirs(out_dir or ".", exist_ok=True)
@@ -146,16 +238,26 @@ def render_video(renderer, width, height, n_frames, fps, output_path, fov, stati
               "disk_rotation_speed": disk_rotation_speed, "orbit_degrees": orbit_degrees}
 
     completed = set()
-    if resume and os.path.isdir(temp_dir) and os.path.isfile(progress_file):
-        with open(progress_file) as f:
-            saved = json.load(f)
-        if saved.get("params", {}) != params:
+    wipe = os.path.isdir(temp_dir) and not resume
+    if resume and os.path.isdir(temp_dir):
+        completed, match = load_progress(temp_dir, params)
+        if not match:
             print("Warning: parameters changed, starting over")
-            if rank == 0:
-                shutil.rmtree(temp_dir)
-        else:
-            completed = set(saved.get("completed", []))
+            completed, wipe = set(), True
+        elif completed:
             print(f"Resuming: {len(completed)}/{n_frames} frames already rendered")
+    if barrier:
+        barrier()                              # every rank has read the old state
+    if wipe:
+        # stale progress files must not be merged into this run: every rank drops its own, rank 0
+        # the merged one and those of ranks a larger, older run had
+        for name in os.listdir(temp_dir):
+            if not (name.startswith("progress.") and name.endswith(".json")):
+                continue
+            mid = name[len("progress."):-len(".json")].strip(".")
+            owner = int(mid) if mid.isdigit() else -1
+            if owner == rank or (rank == 0 and (owner < 0 or owner >= world_size)):
+                os.remove(os.path.join(temp_dir, name))
     if barrier:
         barrier()
     os.makedirs(temp_dir, exist_ok=True)
@@ -166,82 +268,52 @@ def render_video(renderer, width, height, n_frames, fps, output_path, fov, stati
     # (tens of ms per 1080p frame and core): use the host's cores for it
     pool = ThreadPoolExecutor(max_workers=int(os.environ.get("BHR_PNG_WORKERS", str(min(16, os.cpu_count() or 2)))))
     png_level = int(os.environ.get("BHR_PNG_LEVEL", "1"))
+    jobs = {}                                  # frame -> future of its PNG file
+    mine_done = set()                          # frames of THIS run whose file is on disk
 
     def save_png(path, img_u8):
-        with open(path, "wb") as f:
+        tmp = path + ".part"
+        with open(tmp, "wb") as f:
             f.write(encode_png(img_u8, png_level))
+        os.replace(tmp, path)                  # a crash never leaves a truncated frame under the final name
 
-    n_r, n_phi = renderer.dtex_h, renderer.dtex_w
-    factories = init_lifecycle_system(renderer, n_r, n_phi, seed=42)
-    dt = disk_rotation_speed
-    if completed:
-        # replay the simulation up to the resume point (render.py:4427-4434); only the host
-        # state and the statistics are stateful, so the device stages run at stats frames only
-        for f in range(max(completed) + 1):
-            advance_lifecycle_frame(renderer, factories, f * dt, dt)
+    def sink(frame, img_u8):
+        jobs[frame] = pool.submit(save_png, os.path.join(temp_dir, f"frame_{frame:04d}.png"), img_u8)
+        return jobs[frame]
 
-    # Pipelined loop: frames are enqueued without waiting (texture kernels, render, D2H into one of
-    # RING pinned buffers) and the host runs up to DEPTH frames ahead of the device (enough queued work to cover
-    # the ticks of a whole block of another rank's frames): it does the
-    # lifecycle ticks / entity packing of the next frames -- and, with several ranks, the ticks of
-    # the frames other ranks own -- while the device works; a frame is retired (waited for, handed
-    # to the PNG pool) when DEPTH newer ones are in flight.
-    RING, DEPTH = 24, 5                        # pinned frames (in flight + being PNG-encoded), run-ahead depth
-    bufs = [renderer.pinned_frame(np.uint8) for _ in range(RING)]
-    busy = [None] * RING                       # PNG job still reading the buffer
-    in_flight = []                             # (frame, slot) enqueued, not yet waited for
+    def harvest():
+        for frame in [f for f, j in jobs.items() if j.done()]:
+            jobs.pop(frame).result()           # (re-raises a failed write)
+            mine_done.add(frame)
 
-    def retire(item):
-        frame_done, slot = item
-        renderer.wait_frame(slot % 8)          # (eight completion-event slots; DEPTH + 1 <= 8 frames in flight)
-        busy[slot] = pool.submit(save_png, os.path.join(temp_dir, f"frame_{frame_done:04d}.png"), bufs[slot])
-        completed.add(frame_done)
+    def write_progress():
+        harvest()
+        mine = sorted(completed | mine_done)    # (what was on disk at start + this rank's frames; files are merged by union)
+        tmp = my_progress + ".part"
+        with open(tmp, "w") as f:
+            json.dump({"params": params, "completed": mine}, f)
+        os.replace(tmp, my_progress)
 
     t_start = time.time()
-    rendered = 0
-    for frame in range(n_frames):
-        t = frame * dt
-        cam_pos = orbit_camera(static_cam_pos, frame, n_frames, orbit_degrees) if orbit else static_cam_pos
-        if frame in completed:
-            continue
-        mine = frame_owner(frame, world_size) == rank
-        if not mine:
-            for f in factories.values():      # keep the RNG streams in step; no device work
-                f.tick(now=t, dt=dt)
-            continue
-        slot = rendered % RING
-        if busy[slot] is not None:
-            busy[slot].result()
-            busy[slot] = None
-        advance_lifecycle_frame(renderer, factories, t, dt, recompute_stats=(frame % STATS_PERIOD == 0))
-        renderer.render_u8_async(cam_pos, fov, bufs[slot], slot % 8, frame=0)
-        in_flight.append((frame, slot))
-        if len(in_flight) > DEPTH:
-            retire(in_flight.pop(0))
-        rendered += 1
+
+    def on_rendered(rendered, frame):
         if rendered % 10 == 0:
-            with open(my_progress, "w") as f:
-                json.dump({"params": params, "completed": sorted(completed)}, f)
+            write_progress()
         if rendered % 100 == 0:
             print(f"  [rank {rank}] frame {frame}/{n_frames}, {rendered / (time.time() - t_start):.1f} frames/s")
-    for item in in_flight:
-        retire(item)
-    pending = [b for b in busy if b is not None]
-    for f in pending:
-        f.result()
+
+    rendered = run_video_frames(renderer, n_frames, fov, static_cam_pos, orbit, orbit_degrees,
+                                disk_rotation_speed, rank, world_size, completed, sink, on_rendered)
     pool.shutdown(wait=True)
-    with open(my_progress, "w") as f:
-        json.dump({"params": params, "completed": sorted(completed)}, f)
+    write_progress()
+    completed |= mine_done
     if barrier:
         barrier()
     if rank != 0:
         return
     if world_size > 1:
-        for r in range(world_size):
-            p = os.path.join(temp_dir, f"progress.{r}.json")
-            if os.path.isfile(p):
-                with open(p) as f:
-                    completed |= set(json.load(f).get("completed", []))
+        merged, _ = load_progress(temp_dir, params)
+        completed |= merged
         with open(progress_file, "w") as f:
             json.dump({"params": params, "completed": sorted(completed)}, f)
     if rendered:

@@ -123,10 +123,17 @@ class Renderer:
 
         W, H = self.width, self.height
         self.image_field = _Field(lambda: self._planar(L.BUF_BG).transpose(2, 1, 0).copy())
-        self.disk_layer_field = _Field(lambda: self._planar(L.BUF_DISK).transpose(2, 1, 0).copy())
+        # disk_layer_field is what the reference's field holds at that point: the ray march's layer,
+        # or -- after a frame that ran _bloom_kernel -- clamp(layer + 0.4 blur) (its in-place add,
+        # render.py:3112-3114; render() itself composites the copy it read before, render.py:3909)
+        self._disk_post_bloom = False
+        self.disk_layer_field = _Field(lambda: self._planar(
+            L.BUF_DISK_POST if self._disk_post_bloom else L.BUF_DISK).transpose(2, 1, 0).copy())
         self.blur_field = _Field(lambda: self._planar(L.BUF_BLUR).transpose(2, 1, 0).copy())
         # final_field[i, j] = frame[H - 1 - j, i]: (W, H, 3) with the y axis flipped for ti.GUI
-        # (_compose_final_kernel, render.py:3285-3300); filled by render_to_field
+        # (_compose_final_kernel, render.py:3285-3300); filled by render_to_field.  The device keeps
+        # the frame row-major (H, W, 3) -- the layout a CUDA-GL / Vulkan interop blit wants -- and
+        # this view applies the reference's index map on read-back
         self.final_field = _Field(lambda: self._download(L.BUF_FINAL, (H, W, 3), np.float32)[::-1]
                                   .transpose(1, 0, 2).copy())
         self.disk_texture_field = _Field(
@@ -140,8 +147,12 @@ class Renderer:
     def __del__(self):
         ctx = getattr(self, "_ctx", None)
         if ctx:
-            self._lib.bhr_destroy(ctx)
+            self._lib.bhr_destroy(ctx)          # (synchronises the context's streams first)
             self._ctx = None
+        # page-locked frames handed out by pinned_frame(): numpy views of them must not be used
+        # after close() / garbage collection of the renderer
+        for p in self.__dict__.pop("_pinned", []):
+            self._lib.bhr_host_free(p)
 
     def close(self):
         self.__del__()
@@ -233,6 +244,7 @@ class Renderer:
         self._check(self._lib.bhr_render(self._ctx, C.byref(cam),
                                          self._flags(skip_differentials, skip_bloom, aux),
                                          out.ctypes.data, None))
+        self._disk_post_bloom = not skip_bloom
         return out
 
     def render_u8(self, cam_pos, fov, frame=0, skip_differentials=False, skip_bloom=False, out=None):
@@ -240,10 +252,12 @@ class Renderer:
         cam = self._camera(cam_pos, fov, frame)
         if out is None:
             out = np.empty((self.height, self.width, 3), dtype=np.uint8)
-        assert out.dtype == np.uint8 and out.flags.c_contiguous
+        assert out.dtype == np.uint8 and out.flags.c_contiguous \
+            and out.shape == (self.height, self.width, 3)
         self._check(self._lib.bhr_render(self._ctx, C.byref(cam),
                                          self._flags(skip_differentials, skip_bloom), None,
                                          out.ctypes.data))
+        self._disk_post_bloom = not skip_bloom
         return out
 
     def render_async(self, cam_pos, fov, out, slot, frame=0, skip_differentials=False, skip_bloom=False):
@@ -252,11 +266,13 @@ class Renderer:
         returns at once.  `wait_frame(slot)` blocks until it is there.  Video loops use it to
         overlap the host's lifecycle work and the frame copies with the device (driver.py)."""
         cam = self._camera(cam_pos, fov, frame)
-        assert out.dtype in (np.uint8, np.float32) and out.flags.c_contiguous
+        assert out.dtype in (np.uint8, np.float32) and out.flags.c_contiguous \
+            and out.shape == (self.height, self.width, 3)
         f32 = out.ctypes.data if out.dtype == np.float32 else None
         u8 = out.ctypes.data if out.dtype == np.uint8 else None
         self._check(self._lib.bhr_render_async(self._ctx, C.byref(cam),
                                                self._flags(skip_differentials, skip_bloom), f32, u8, int(slot)))
+        self._disk_post_bloom = not skip_bloom
 
     def render_u8_async(self, cam_pos, fov, out, slot, frame=0, skip_differentials=False, skip_bloom=False):
         assert out.dtype == np.uint8
@@ -271,17 +287,23 @@ class Renderer:
         cam = self._camera(cam_pos, fov, frame)
         self._check(self._lib.bhr_render(self._ctx, C.byref(cam),
                                          self._flags(skip_differentials, skip_bloom, aux), None, None))
+        self._disk_post_bloom = not skip_bloom
 
     def render_to_field(self, cam_pos, fov, frame=0, skip_differentials=False, skip_bloom=False):
         """render_to_field (render.py:3819-3863): the frame stays on the device (no host copy, no
         synchronisation, no lens flare); `final_field.to_numpy()` reads it back in the reference's
-        (W, H, 3), y-flipped layout."""
+        (W, H, 3), y-flipped layout.  Unlike render(), the reference composites the disk layer AFTER
+        _bloom_kernel's in-place `disk = clamp(disk + 0.4 blur)` (render.py:3112-3114, 3857-3863):
+        final = clamp(bg + clamp(disk + 0.4 blur) + blur) -- flag BHR_FIELD_COMPOSITE."""
         cam = self._camera(cam_pos, fov, frame)
         self._check(self._lib.bhr_render(self._ctx, C.byref(cam),
-                                         self._flags(skip_differentials, skip_bloom) | L.SKIP_FLARE, None, None))
+                                         self._flags(skip_differentials, skip_bloom) | L.SKIP_FLARE
+                                         | L.FIELD_COMPOSITE, None, None))
+        self._disk_post_bloom = not skip_bloom
 
     def pinned_frame(self, dtype=np.float32):
-        """A page-locked (H, W, 3) array for `render(..., out=)` / `render_u8(..., out=)`."""
+        """A page-locked (H, W, 3) array for `render(..., out=)` / `render_u8(..., out=)`; owned by
+        the renderer and released by close() (copy what has to outlive it)."""
         n = self.height * self.width * 3 * np.dtype(dtype).itemsize
         p = C.c_void_p()
         if self._lib.bhr_host_alloc(n, C.byref(p)) != 0:
@@ -301,6 +323,12 @@ class Renderer:
         self._check(self._lib.bhr_last_total_steps(self._ctx, C.byref(v)))
         return v.value
 
+    def launch_count(self):
+        """Kernels this context has launched so far (render path, texture pipeline, peer flags)."""
+        v = C.c_uint64()
+        self._check(self._lib.bhr_launch_count(self._ctx, C.byref(v)))
+        return v.value
+
     def last_retrace_count(self):
         v = C.c_uint32()
         self._check(self._lib.bhr_last_retrace_count(self._ctx, C.byref(v)))
@@ -309,7 +337,7 @@ class Renderer:
     def last_stage_ms(self):
         arr = (C.c_float * 5)()
         self._check(self._lib.bhr_last_stage_ms(self._ctx, arr))
-        return dict(zip(("ray_march", "bloom_h", "bloom_v_composite", "gap", "total"), list(arr)))
+        return dict(zip(("ray_march", "bloom_h", "bloom_v_composite", "flare", "total"), list(arr)))
 
     # ------------------------------------------------------------------ disk-texture pipeline
     def init_background_layer(self, n_r, n_phi, seed=42):

@@ -64,6 +64,12 @@ typedef struct {
 #define BHR_SKIP_BLOOM 2u           /* render(skip_bloom=True), render.py:3911         */
 #define BHR_WANT_AUX 4u             /* also fill the class / step-count buffers        */
 #define BHR_SKIP_FLARE 8u           /* render_to_field (render.py:3819-3863) never applies the lens flare */
+/* render_to_field's compositing (render.py:3857-3863 after _bloom_kernel's in-place add, 3112-3114):
+ * final = clamp(bg + clamp(disk + 0.4 blur, 0, 1) + blur, 0, 1) instead of render()'s clamp(bg + disk + blur) */
+#define BHR_FIELD_COMPOSITE 16u
+/* bhr_render_rows_stage2: take the frame-wide flare sums from device buffer BHR_BUF_FLARE_SUMS (filled by
+ * bhr_flare_sums_device and, with several GPUs, all-reduced in place by the caller) instead of a host array */
+#define BHR_FLARE_FROM_DEVICE 32u
 
 /* device buffers that can be inspected / exchanged (bhr_buffer, bhr_download) */
 typedef enum {
@@ -77,7 +83,10 @@ typedef enum {
     BHR_BUF_DISK_TEX = 7,  /* disk_texture_field: (n_r, n_phi, 4) f32                    */
     BHR_BUF_DISK_MIPS = 8, /* compact pyramid, level l = (n_r>>l, n_phi>>l, 4) f32       */
     BHR_BUF_COMP = 9,      /* _comp_field: (13, n_r, n_phi) f32                          */
-    BHR_BUF_BLUR = 10      /* blur_field (after the vertical pass): planar 3 x (H, W)    */
+    BHR_BUF_BLUR = 10,     /* blur_field (after the vertical pass): planar 3 x (H, W)    */
+    BHR_BUF_FLARE_SUMS = 12, /* 3 f64 {sum B, sum x*B, sum y*B} of the last bhr_flare_sums[_device] call       */
+    BHR_BUF_DISK_POST = 11 /* disk_layer_field as _bloom_kernel leaves it (render.py:3112-3114): clamp(disk + 0.4 blur, 0, 1),
+                              planar 3 x (H, W); formed on demand by bhr_download (bhr_buffer does not expose it) */
 } bhr_buffer_id;
 
 /* ---- lifecycle (TaichiRenderer.__init__, render.py:2199-2290) ---- */
@@ -105,6 +114,9 @@ int bhr_set_option(bhr_ctx* ctx, const char* key, double value);
 /* pinned host memory so that frame read-back DMA needs no staging copy */
 int bhr_host_alloc(size_t bytes, void** out);
 int bhr_host_free(void* p);
+/* "dddd:bb:dd.f" of a CUDA device: lets the host find the GPU's NUMA node in sysfs and place its
+ * threads / pinned frame buffers there (black_hole_renderer_b200/hostmem.py) */
+int bhr_device_pci_bus_id(int device, char* out, int len);
 /* page-lock caller-owned memory, e.g. a shared-memory frame every rank copies its rows into */
 int bhr_host_register(void* p, size_t bytes);
 int bhr_host_unregister(void* p);
@@ -139,6 +151,8 @@ int bhr_render_rows_stage1(bhr_ctx* ctx, const bhr_camera* cam, uint32_t flags, 
 int bhr_render_rows_stage2(bhr_ctx* ctx, uint32_t flags, int row0, int row1,
                            const double* flare_sums /* NULL or {sum B, sum x*B, sum y*B} */);
 int bhr_flare_sums(bhr_ctx* ctx, int row0, int row1, double out[3]);
+/* the same reduction, enqueued only: the sums stay in BHR_BUF_FLARE_SUMS (no host synchronisation) */
+int bhr_flare_sums_device(bhr_ctx* ctx, int row0, int row1);
 int bhr_bloom_radius(const bhr_ctx* ctx);
 
 /* ---- the same split with peer memory instead of NCCL (one process per GPU on one node) ----
@@ -152,12 +166,23 @@ int bhr_bloom_radius(const bhr_ctx* ctx);
  * processes, page-locked with bhr_host_register) each rank copies its own rows to the host over
  * its own PCIe link instead, and rank 0 returns when all of them have landed.
  * No collective library, no host synchronisation between the stages; every rank must call it once
- * per frame, all with or all (but rank 0) without host buffers. */
+ * per frame, all with or all (but rank 0) without host buffers.
+ * Failure behaviour: no wait spins for ever.  A rank that cannot finish a frame poisons it (its
+ * peers drain and return BHR_ERR_STATE); a flag that does not arrive within option
+ * "peer_timeout_ms" (default 20 000: a rank died or the ranks called an unequal number of times)
+ * ends the wait, and the call that next synchronises returns BHR_ERR_STATE. */
 typedef struct { unsigned char bytes[64]; } bhr_ipc_handle;
 int bhr_peer_export(bhr_ctx* ctx, bhr_ipc_handle out[4]);
 int bhr_peer_attach(bhr_ctx* ctx, int rank, int world, const bhr_ipc_handle* all);
 int bhr_render_tiled_peer(bhr_ctx* ctx, const bhr_camera* cam, uint32_t flags, float* out_f32, uint8_t* out_u8);
 int bhr_peer_set_distributed_egress(bhr_ctx* ctx, int enabled);   /* all ranks, before the first frame */
+/* Tile boundaries (world + 1 ints, bounds[0] = 0, bounds[world] = H): rank r renders rows
+ * [bounds[r], bounds[r + 1]).  Equal heights by default; every rank must install the same bounds
+ * before the same frame.  Rows through the hole and the disk cost more than sky rows, so a caller
+ * balances the tiles by cost: bhr_row_costs returns, for the rows of the last frame rendered with
+ * BHR_WANT_AUX, the RK4 evaluations per row. */
+int bhr_peer_set_tiles(bhr_ctx* ctx, const int* bounds);
+int bhr_row_costs(bhr_ctx* ctx, int row0, int row1, uint64_t* out /* row1 - row0 */);
 int bhr_peer_detach(bhr_ctx* ctx);
 
 /* ---- device buffers ---- */
@@ -165,6 +190,9 @@ int bhr_buffer(bhr_ctx* ctx, int id, void** dev_ptr, size_t* bytes);
 int bhr_download(bhr_ctx* ctx, int id, void* host, size_t bytes);
 /* total RK4 evaluations of the last ray march (sum over pixels); feeds the flop count */
 int bhr_last_total_steps(bhr_ctx* ctx, uint64_t* out);
+/* kernels of this library launched by the context since bhr_create (render path, texture pipeline,
+ * peer flags; the statistics / test hooks are not counted) -- what bench.py reports as gpu_launches */
+int bhr_launch_count(bhr_ctx* ctx, uint64_t* out);
 /* number of rays the last ray march re-traced with the exactly-rounded integrator */
 int bhr_last_retrace_count(bhr_ctx* ctx, uint32_t* out);
 /* device time (ms, CUDA events) of the stages of the last bhr_render: {ray march, bloom H,

@@ -277,6 +277,12 @@ enum { TERM_EXHAUSTED = 0, TERM_HORIZON = 1, TERM_ESCAPED = 2 };
  * Outputs: bg[3], disk[3]; *term, *nhits (crossings inside [r_inner, r_outer]), *steps = number
  * of RK4 evaluations including the terminating one (SURVEY.md 8d flop accounting).
  */
+/* diagnostic output for the parity tests: when set, trace_pixel stores the escape direction of
+ * every pixel ((H, W, 3), zeros for rays that do not escape) -- the sky lookup's input, which
+ * tells a pole-direction outlier (d phi = d dir / sin theta) from a real difference */
+static float *g_escape_dir_out = NULL;
+void orc_set_escape_dir_out(float *p) { g_escape_dir_out = p; }
+
 static void trace_pixel(const orc_scene *s, const float *sky, const float *tex, const float *mips,
                         int i, int j, float bg[3], float disk[3], uint8_t *term, uint8_t *nhits,
                         int32_t *steps)
@@ -418,6 +424,10 @@ static void trace_pixel(const orc_scene *s, const float *sky, const float *tex, 
     disk[0] = f_clamp(accum.x, 0.0f, 1.0f);
     disk[1] = f_clamp(accum.y, 0.0f, 1.0f);
     disk[2] = f_clamp(accum.z, 0.0f, 1.0f);
+    if (g_escape_dir_out) {
+        float *e = g_escape_dir_out + ((size_t)j * s->width + i) * 3;
+        e[0] = esc_dir.x; e[1] = esc_dir.y; e[2] = esc_dir.z;
+    }
     *term = horizon ? TERM_HORIZON : (escaped ? TERM_ESCAPED : TERM_EXHAUSTED);
     *nhits = (uint8_t)(hits > 255 ? 255 : hits);
     *steps = evals;

@@ -15,6 +15,12 @@ the reference's own kernels / host code:
   noise.npz        eval_noise (render.py:3769) simplex + fbm samples
   texture_pipeline.npz  _init_lifecycle_system + _advance_lifecycle_frame (render.py:4079-4153):
                    comp field, stats, composed RGBA texture, mip pyramid
+  render_to_field.npz   TaichiRenderer.render_to_field() (render.py:3819-3863) on two of the
+                   raymarch_* cases: final_field (W, H, 3) y-flipped, with and without bloom, and
+                   the disk layer field it leaves behind
+  shifted_compose.npz  the legacy parametric path's numpy side, _generate_disk_texture_rotating_from_state
+                   (render.py), at t_offset in {0, 5, 50, 180} -- what the reference's
+                   tests/unit/test_gpu_texture_compose.py:55-105 compares the compose kernel with
   host.npz         build_camera, compute_disk_texture_resolution, generate_skybox,
                    EntityFactory parameter streams (render.py:93, 1128, 153, 624)
 """
@@ -108,6 +114,47 @@ def gen_raymarch(name, c):
         r.lens_flare = lf
     print(f"  {name}: {time.time() - t0:.1f}s  final mean={final.mean():.5f}")
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+
+
+def gen_render_to_field():
+    """render_to_field (render.py:3819-3863): ray march -> _bloom_kernel (in-place
+    disk = clamp(disk + 0.4 blur), render.py:3112-3114) -> _compose_final_kernel
+    (bg + disk + blur, y-flipped, render.py:3285-3300); no lens flare."""
+    out = {}
+    for name in ("raymarch_default", "raymarch_aa_tilt_flare"):
+        c = RAY_CASES[name]
+        skybox = ref.generate_skybox(tex_w=128, tex_h=64, seed=7, n_stars=300)
+        disk = smooth_disk_texture(c["dtex"][0], c["dtex"][1], seed=11)
+        r = ref.TaichiRenderer(c["w"], c["h"], skybox, disk, step_size=c["step"], r_max=c["r_max"],
+                               device="cpu", r_disk_inner=c["r_in"], r_disk_outer=c["r_out"],
+                               disk_tilt=c["tilt"], lens_flare=c["flare"], anti_alias=c["aa"],
+                               aa_strength=c["aa_strength"])
+        t0 = time.time()
+        r.render_to_field(c["pov"], c["fov"], frame=0)
+        out[name + "/final_field"] = r.final_field.to_numpy()                  # (W, H, 3)
+        out[name + "/disk_layer_field"] = r.disk_layer_field.to_numpy()        # (W, H, 3) post-bloom
+        r.render_to_field(c["pov"], c["fov"], frame=0, skip_bloom=True)
+        out[name + "/final_field_skip_bloom"] = r.final_field.to_numpy()
+        out[name + "/disk_layer_field_skip_bloom"] = r.disk_layer_field.to_numpy()
+        print(f"  render_to_field {name}: {time.time() - t0:.1f}s")
+    np.savez_compressed(os.path.join(OUT, "render_to_field.npz"), **out)
+
+
+def gen_shifted_compose():
+    """Legacy parametric path, numpy side (render.py:988-1024): the state's 13 component planes
+    rolled per row by the Keplerian shift and composed -- the array the reference's
+    tests/unit/test_gpu_texture_compose.py:55-105 holds the compose kernel to (< 1e-4)."""
+    n_phi, n_r = 256, 64
+    st = ref.build_disk_texture_rotating_state(n_phi=n_phi, n_r=n_r, seed=42, r_inner=2.0, r_outer=15.0,
+                                               enable_rt=True, generation_scale=1)
+    out = dict(n_phi=np.array([n_phi]), n_r=np.array([n_r]), enable_rt=np.array([int(st.enable_rt)]),
+               color_temp=np.array([st.color_temp]), omega_rows=st.omega_rows, edge=st.edge)
+    for k in ("temp_base", "spiral", "spiral_temp", "turbulence", "turb_temp", "arcs", "arcs_temp",
+              "rt_spikes", "rt_temp", "hotspot", "hotspot_temp", "az_hotspot", "disturb_mod"):
+        out["state_" + k] = getattr(st, k)
+    for t in (0.0, 5.0, 50.0, 180.0):
+        out[f"tex_t{t:g}"] = ref._generate_disk_texture_rotating_from_state(st, t_offset=t)
+    np.savez_compressed(os.path.join(OUT, "shifted_compose.npz"), **out)
 
 
 def _tiny_renderer(n_r=16, n_phi=64, r_in=2.0, r_out=15.0):
@@ -234,6 +281,8 @@ def main():
     jobs["noise"] = gen_noise
     jobs["texture_pipeline"] = gen_texture_pipeline
     jobs["host"] = gen_host
+    jobs["render_to_field"] = gen_render_to_field
+    jobs["shifted_compose"] = gen_shifted_compose
     for name, fn in jobs.items():
         if a.only and a.only != name:
             continue

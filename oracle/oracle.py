@@ -67,6 +67,8 @@ def lib():
                                           C.c_int, C.c_float, fp]
         L.orc_build_mips.restype = None
         L.orc_build_mips.argtypes = [fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, fp]
+        L.orc_set_escape_dir_out.restype = None
+        L.orc_set_escape_dir_out.argtypes = [C.c_void_p]
         L.orc_num_threads.restype = C.c_int
         L.orc_set_num_threads.argtypes = [C.c_int]
         _lib = L
@@ -131,8 +133,9 @@ def build_mips(base, levels=5, numpy_order=True, zero_pad=True):
     return mips
 
 
-def ray_march(scene, skybox, disk_tex, mips=None, rows=None, want_aux=True):
-    """_ray_march_kernel, render.py:2787-3018.  Returns dict(bg, disk, term, nhits, steps, total)."""
+def ray_march(scene, skybox, disk_tex, mips=None, rows=None, want_aux=True, want_escape_dir=False):
+    """_ray_march_kernel, render.py:2787-3018.  Returns dict(bg, disk, term, nhits, steps, total
+    [, escape_dir (H, W, 3): the direction the sky lookup used, zeros for captured rays])."""
     skybox, disk_tex = _f32c(skybox), _f32c(disk_tex)
     if mips is None:
         mips = build_mips(disk_tex, scene.num_mip_levels)
@@ -144,10 +147,18 @@ def ray_march(scene, skybox, disk_tex, mips=None, rows=None, want_aux=True):
     term = np.zeros((H, W), dtype=np.uint8)
     nhits = np.zeros((H, W), dtype=np.uint8)
     steps = np.zeros((H, W), dtype=np.int32)
-    total = lib().orc_ray_march(C.byref(scene), _fp(skybox), _fp(disk_tex), _fp(mips), r0, r1,
-                                _fp(bg), _fp(disk), term.ctypes.data, nhits.ctypes.data,
-                                steps.ctypes.data)
-    return dict(bg=bg, disk=disk, term=term, nhits=nhits, steps=steps, total_steps=int(total))
+    esc = np.zeros((H, W, 3), dtype=np.float32) if want_escape_dir else None
+    lib().orc_set_escape_dir_out(esc.ctypes.data if esc is not None else None)
+    try:
+        total = lib().orc_ray_march(C.byref(scene), _fp(skybox), _fp(disk_tex), _fp(mips), r0, r1,
+                                    _fp(bg), _fp(disk), term.ctypes.data, nhits.ctypes.data,
+                                    steps.ctypes.data)
+    finally:
+        lib().orc_set_escape_dir_out(None)
+    out = dict(bg=bg, disk=disk, term=term, nhits=nhits, steps=steps, total_steps=int(total))
+    if esc is not None:
+        out["escape_dir"] = esc
+    return out
 
 
 def bloom(disk_layer, width=None):
@@ -189,10 +200,10 @@ def to_u8(img):
 
 
 def render(width, height, cam_pos, fov, skybox, disk_tex, mips=None, lens_flare_on=False,
-           skip_bloom=False, **kw):
+           skip_bloom=False, want_escape_dir=False, **kw):
     """TaichiRenderer.render, render.py:3865-3923.  Returns dict with every intermediate."""
     sc = make_scene(width, height, cam_pos, fov, skybox.shape, disk_tex.shape, **kw)
-    rm = ray_march(sc, skybox, disk_tex, mips)
+    rm = ray_march(sc, skybox, disk_tex, mips, want_escape_dir=want_escape_dir)
     if skip_bloom:
         rm["blur"] = None
         final = composite(rm["bg"], rm["disk"])
@@ -203,6 +214,25 @@ def render(width, height, cam_pos, fov, skybox, disk_tex, mips=None, lens_flare_
         final, rm["centroid"] = lens_flare(final, rm["disk"])
     rm["final"] = final
     return rm
+
+
+def render_to_field(width, height, cam_pos, fov, skybox, disk_tex, mips=None, skip_bloom=False, **kw):
+    """TaichiRenderer.render_to_field, render.py:3819-3863: ray march, _bloom_kernel INCLUDING its
+    in-place tail `disk = clamp(disk + 0.4 blur, 0, 1)` (render.py:3112-3114; f32 multiply, then
+    add), then _compose_final_kernel (render.py:3285-3300): clamp((bg + disk) + blur, 0, 1) -- or
+    clamp(bg + disk) without bloom -- stored y-flipped as (W, H, 3).  No lens flare on this path.
+    Returns dict(final_field (W, H, 3), disk_layer_field (W, H, 3), frame (H, W, 3))."""
+    sc = make_scene(width, height, cam_pos, fov, skybox.shape, disk_tex.shape, **kw)
+    rm = ray_march(sc, skybox, disk_tex, mips)
+    bg, disk = rm["bg"], rm["disk"]
+    if skip_bloom:
+        frame = np.clip(bg + disk, np.float32(0), np.float32(1))
+    else:
+        blur = bloom(disk, width)
+        disk = np.clip(disk + blur * np.float32(0.4), np.float32(0), np.float32(1))
+        frame = np.clip((bg + disk) + blur, np.float32(0), np.float32(1))
+    return dict(final_field=np.ascontiguousarray(frame[::-1].transpose(1, 0, 2)),
+                disk_layer_field=np.ascontiguousarray(disk.transpose(1, 0, 2)), frame=frame)
 
 
 def eval_noise(coords, mode="simplex", octaves=4, persistence=0.5, lacunarity=2.0):

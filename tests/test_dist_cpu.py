@@ -25,28 +25,31 @@ def _truth(C, H, W):
     return 1000 * c + y + 0.001 * x
 
 
-def _worker(rank, world, port, H, W, radius, result_dir):
+def _worker(rank, world, port, H, W, radius, result_dir, bounds=None):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from black_hole_renderer_b200.dist import exchange_halos, gather_rows, tile_rows
+    from black_hole_renderer_b200.dist import equal_bounds, exchange_halos, gather_rows
     C = 3
     truth = _truth(C, H, W)
-    row0, row1 = tile_rows(H, world, rank)
+    b = bounds or equal_bounds(H, world)
+    row0, row1 = b[rank], b[rank + 1]
     plane = torch.full((C, H, W), -1.0)
     plane[:, row0:row1] = truth[:, row0:row1]
-    exchange_halos(plane, H, radius, rank, world)
+    exchange_halos(plane, H, radius, rank, world, bounds=bounds)
     lo, hi = max(row0 - radius, 0), min(row1 + radius, H)
     ok = bool(torch.equal(plane[:, lo:hi], truth[:, lo:hi]))
     # rows outside tile + halo must be untouched
     untouched = bool((plane[:, :lo] == -1).all() and (plane[:, hi:] == -1).all())
     tile = truth[0, row0:row1].unsqueeze(-1).repeat(1, 1, 3).contiguous()
-    full = gather_rows(tile, H, rank, world, 0)
-    gathered = True
-    if rank == 0:
-        gathered = bool(torch.equal(full, truth[0].unsqueeze(-1).repeat(1, 1, 3)))
-    else:
-        gathered = full is None
+    want = truth[0].unsqueeze(-1).repeat(1, 1, 3)
+    full = gather_rows(tile, H, rank, world, 0, bounds=bounds)
+    gathered = bool(torch.equal(full, want)) if rank == 0 else full is None
+    # receiving straight into the frame whose own rows the tile aliases (no concatenation)
+    frame = torch.full((H, W, 3), -2.0)
+    frame[row0:row1] = tile
+    full = gather_rows(frame[row0:row1], H, rank, world, 0, bounds=bounds, out=frame if rank == 0 else None)
+    gathered = gathered and (bool(torch.equal(full, want)) if rank == 0 else full is None)
     with open(os.path.join(result_dir, f"r{rank}"), "w") as f:
         f.write(f"{int(ok)}{int(untouched)}{int(gathered)}")
     dist.barrier()
@@ -60,6 +63,36 @@ def test_halo_exchange_and_gather_gloo(tmp_path, world, H, radius):
     mp.spawn(_worker, args=(world, port, H, 16, radius, str(tmp_path)), nprocs=world, join=True)
     for r in range(world):
         assert open(tmp_path / f"r{r}").read() == "111", r
+
+
+@pytest.mark.parametrize("world,H,radius,bounds", [(3, 48, 10, [0, 30, 36, 48]), (2, 40, 6, [0, 9, 40])])
+def test_halo_exchange_and_gather_with_cost_balanced_tiles(tmp_path, world, H, radius, bounds):
+    """Uneven tile heights (cost-balanced split), one of them shorter than the halo radius."""
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, H, 16, radius, str(tmp_path), bounds), nprocs=world, join=True)
+    for r in range(world):
+        assert open(tmp_path / f"r{r}").read() == "111", r
+
+
+def test_balanced_bounds_equalise_the_cost():
+    from black_hole_renderer_b200.dist import balanced_bounds, equal_bounds
+    rng = np.random.default_rng(0)
+    H = 2160
+    y = np.arange(H)
+    cost = 3840 * (70 + 60 * np.exp(-((y - 1080) / 300.0) ** 2)) + rng.integers(0, 1000, H)
+    for world in (1, 2, 4, 8):
+        b = balanced_bounds(cost, world, min_rows=8)
+        assert b[0] == 0 and b[-1] == H and len(b) == world + 1 and all(b[i + 1] - b[i] >= 8 for i in range(world))
+        per = [cost[b[i]:b[i + 1]].sum() for i in range(world)]
+        eq = equal_bounds(H, world)
+        per_eq = [cost[eq[i]:eq[i + 1]].sum() for i in range(world)]
+        assert max(per) <= max(per_eq) * 1.002
+        assert max(per) / (sum(per) / world) < 1.02
+    # degenerate profiles still give valid, ordered bounds
+    b = balanced_bounds(np.zeros(64), 4, min_rows=8)
+    assert b[0] == 0 and b[-1] == 64 and all(b[i + 1] - b[i] >= 8 for i in range(4))
+    b = balanced_bounds(np.r_[np.zeros(60), 1e9, np.zeros(3)], 4, min_rows=8)
+    assert b[0] == 0 and b[-1] == 64 and all(b[i + 1] - b[i] >= 8 for i in range(4))
 
 
 def test_tile_rows_partition():

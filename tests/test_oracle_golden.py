@@ -50,6 +50,57 @@ def test_skip_flags_match_reference(name):
         assert np.abs(r["final"] - d["final_skip_diff"]).max() <= TOL
 
 
+@pytest.mark.parametrize("name", ["raymarch_default", "raymarch_aa_tilt_flare"])
+def test_render_to_field_matches_reference(name):
+    """render_to_field (render.py:3819-3863) run by the reference itself: final_field is
+    clamp(bg + clamp(disk + 0.4 blur) + blur), y-flipped (W, H, 3), never flared; the disk layer
+    field is left in its post-bloom state."""
+    d = np.load(os.path.join(GOLDEN, name + ".npz"))
+    g = np.load(os.path.join(GOLDEN, "render_to_field.npz"))
+    p = d["params"]
+    kw = dict(step_size=p[6], r_max=p[7], r_inner=p[8], r_outer=p[9], disk_tilt=p[10],
+              anti_alias="lod_radius" if p[12] else "disabled", aa_strength=p[13])
+    for skip, suffix in ((False, ""), (True, "_skip_bloom")):
+        r = O.render_to_field(int(p[0]), int(p[1]), p[2:5], p[5], d["skybox"], d["disk_tex"], mips=d["mips"],
+                              skip_bloom=skip, **kw)
+        assert r["final_field"].shape == g[name + "/final_field" + suffix].shape == (int(p[0]), int(p[1]), 3)
+        assert np.abs(r["final_field"] - g[name + "/final_field" + suffix]).max() <= TOL
+        assert np.abs(r["disk_layer_field"] - g[name + "/disk_layer_field" + suffix]).max() <= TOL
+    # it is NOT render()'s frame: the disk layer enters with 1.4 x its bloom (SURVEY.md T6)
+    assert np.abs(g[name + "/final_field"][:, ::-1].transpose(1, 0, 2) - d["final"]).max() > 1e-3
+
+
+def test_shifted_compose_matches_the_reference_numpy_generator():
+    """Legacy parametric path (f4): the oracle's compose with a Keplerian row shift against the
+    reference's numpy _generate_disk_texture_rotating_from_state (render.py:988-1024) at the offsets
+    its own test uses (tests/unit/test_gpu_texture_compose.py:98-112, tolerance 1e-4 there)."""
+    g = np.load(os.path.join(GOLDEN, "shifted_compose.npz"))
+    names = ["temp_base", "spiral", "spiral_temp", "turbulence", "turb_temp", "arcs", "arcs_temp",
+             "rt_spikes", "rt_temp", "hotspot", "hotspot_temp", "az_hotspot", "disturb_mod"]
+    comp = np.stack([g["state_" + k] for k in names]).astype(np.float32)
+    stats, rows = parametric_stats(comp, g["edge"], bool(g["enable_rt"][0]))
+    for t in (0.0, 5.0, 50.0, 180.0):
+        want = g[f"tex_t{t:g}"]
+        got = O.compose_texture(comp, g["omega_rows"], g["edge"], stats, rows, t_offset=t,
+                                enable_rt=int(g["enable_rt"][0]), color_temp=float(g["color_temp"][0]))
+        assert np.abs(got - want).max() < 1e-4, t
+    assert np.abs(g["tex_t50"] - g["tex_t0"]).max() > 0.05       # (the offsets do move the texture)
+
+
+def parametric_stats(comp, edge, enable_rt=True):
+    """upload_parametric_state's statistics, render.py:2363-2379: raw percentiles of the unrotated
+    state (no floors, no base-temperature term)."""
+    rt_w = 0.20 if enable_rt else 0.0
+    density = (0.15 + 0.10 * comp[1] + 0.30 * comp[3] + 0.20 * comp[9] + 0.30 * comp[5] + rt_w * comp[7]) * comp[12]
+    density *= edge[:, None]
+    ts = (comp[2] + comp[4] + comp[6] + comp[8] + comp[10]) * comp[12]
+    scale = float(np.percentile(ts[ts > 0], 95))
+    tss = np.clip(ts / (scale + 1e-6) * 0.8, 0, 1.2)
+    stats = np.array([float(np.percentile(density, 98)), scale], dtype=np.float32)
+    rows = np.stack([np.max(tss, axis=1), np.quantile(tss, 0.7, axis=1)], axis=1).astype(np.float32)
+    return stats, rows
+
+
 def test_mip_pyramid_matches_numpy_generator():
     d = np.load(os.path.join(GOLDEN, "raymarch_aa_tilt_flare.npz"))
     assert np.array_equal(O.build_mips(d["disk_tex"], 5, numpy_order=True), d["mips"])

@@ -41,9 +41,11 @@ def test_strict_mode_matches_reference_goldens(name):
     img = r.render(pov, fov)
     assert np.abs(img - d["final"]).max() < 2e-5
     assert np.abs(r.image_field.to_numpy().transpose(1, 0, 2) - d["bg"]).max() < 2e-5
-    assert np.abs(r.disk_layer_field.to_numpy().transpose(1, 0, 2) - d["disk_layer"]).max() < 2e-5
+    # (after a bloomed frame the field holds clamp(layer + 0.4 blur), render.py:3112-3114)
+    assert np.abs(r.disk_layer_field.to_numpy().transpose(1, 0, 2) - d["disk_layer_after_bloom"]).max() < 2e-5
     assert np.abs(r.blur_field.to_numpy().transpose(1, 0, 2) - d["blur"]).max() < 2e-5
     assert np.abs(r.render(pov, fov, skip_bloom=True) - d["final_skip_bloom"]).max() < 2e-5
+    assert np.abs(r.disk_layer_field.to_numpy().transpose(1, 0, 2) - d["disk_layer"]).max() < 2e-5
     if "final_skip_diff" in d.files:
         r.lens_flare = False
         img = r.render(pov, fov, skip_differentials=True, skip_bloom=True)
@@ -148,12 +150,17 @@ def test_camera_on_the_axis():
     _check_gate(r, ref, pov, fov, max_class_frac=2e-4)
 
 
-def _check_gate_full_size(r, ref, pov, fov):
+def _check_gate_full_size(r, ref, pov, fov, max_outliers, max_outlier_delta):
     """The gate at BASELINE.json's full sizes.  Besides (termination, hit count) a pixel's class
     includes the index of its terminating RK4 step: a ray whose radius lands within an ulp of the
     escape radius terminates one step earlier or later than the reference's, which moves the
     escape direction by one step of curvature -- a classification boundary in the north star's
-    sense (<= 0.01 % of pixels).  The 8-bit bound is asserted on every pixel whose class agrees."""
+    sense (<= 0.01 % of pixels).  The 8-bit bound is asserted on every pixel whose class agrees,
+    except for a counted, bounded and EXPLAINED residue: sky pixels whose escape direction points
+    at a pole of the equirectangular sky (|dir.z| > 0.99), where d(phi) = d(dir) / sin(theta) turns
+    one ulp of the direction into a sub-texel shift across a star.  Every outlier is required to be
+    such a pixel, their number and their largest |delta| are bounded, and the report is printed so
+    that a regression (1 px -> 8 px, delta 3 -> 200) is visible."""
     img = r.render(pov, fov, aux=True)
     cls, steps = r.last_aux()
     cls = cls & 31
@@ -166,27 +173,77 @@ def _check_gate_full_size(r, ref, pov, fov):
     g8 = (np.clip(img, 0, 1) * np.float32(255)).astype(np.uint8).astype(np.int32)
     r8 = (np.clip(ref["final"], 0, 1) * np.float32(255)).astype(np.uint8).astype(np.int32)
     d = np.abs(g8 - r8).max(axis=-1)
+    rep["boundary_pixels"] = int(boundary.sum())
     rep["boundary_frac"] = float(boundary.mean())
     rep["max_u8_non_boundary"] = int(d[~boundary].max())
     rep["n_gt1_non_boundary"] = int((d[~boundary] > 1).sum())
+    out = np.argwhere((d > 2) & ~boundary)
+    ez = ref["escape_dir"][..., 2]
+    rep["outliers"] = [dict(y=int(y), x=int(x), delta=int(d[y, x]), term=int(ref["term"][y, x]),
+                            escape_dir_z=float(ez[y, x])) for y, x in out]
+    print("full-size parity report:", {k: v for k, v in rep.items()})
     assert rep["class_flip_frac"] <= 1e-4, rep
     assert rep["boundary_frac"] <= 1e-4, rep
     assert rep["psnr"] >= 45.0, rep
+    assert len(out) <= max_outliers, rep
+    for o in rep["outliers"]:
+        assert o["term"] == 2 and abs(o["escape_dir_z"]) > 0.99 and o["delta"] <= max_outlier_delta, (o, rep)
     return rep, d, boundary
+
+
+_FHD = {}
+
+
+def _fhd_default_case():
+    """configs[1] at full size: renderer, inputs and ONE oracle frame shared by the tests below."""
+    if not _FHD:
+        r, sky, tex, pov, fov, W, H = _scene("fhd")
+        okw = dict(step_size=0.1, r_max=10.0, r_inner=2.0, r_outer=15.0)
+        ref = O.render(W, H, pov, fov, sky, tex, want_escape_dir=True, **okw)
+        _FHD.update(r=r, sky=sky, tex=tex, pov=pov, fov=fov, W=W, H=H, ref=ref)
+    return _FHD
 
 
 def test_config2_fhd_full_size_against_the_oracle():
     """BASELINE.json configs[1] at full size (1920 x 1080, 2.07 M rays) against the CPU oracle."""
-    r, sky, tex, pov, fov, W, H = _scene("fhd")
-    ref = _oracle(W, H, pov, fov, sky, tex, {})
-    rep, d, boundary = _check_gate_full_size(r, ref, pov, fov)
-    # Known residue (DESIGN.md 2): a ray that leaves towards a pole of the equirectangular sky has
-    # d(phi) = d(direction) / sin(theta), so an ulp of the escape direction moves the lookup across
-    # sub-texel stars; no implementation that is not bit-identical to the reference's float
-    # sequence can bound those pixels.  <= 1e-6 of the frame (1 pixel measured).
-    assert int((d[~boundary] > 2).sum()) <= 2, rep
+    c = _fhd_default_case()
+    r, ref = c["r"], c["ref"]
+    r.set_option("raymarch_mode", 0)
+    rep, d, boundary = _check_gate_full_size(r, ref, c["pov"], c["fov"], max_outliers=2, max_outlier_delta=48)
     assert r.last_total_steps() == int(r.last_aux()[1].sum())
     assert abs(r.last_total_steps() - ref["total_steps"]) <= 1e-3 * ref["total_steps"]
+
+
+def test_config2_fhd_full_size_strict_mode_is_the_oracle_trajectory():
+    """The strict integrator (reference operation order, exactly rounded) at full fhd size: no
+    class flip and the SAME number of RK4 evaluations for every one of the 2.07 M rays."""
+    c = _fhd_default_case()
+    r, ref = c["r"], c["ref"]
+    r.set_option("raymarch_mode", 2)
+    try:
+        img = r.render(c["pov"], c["fov"], aux=True)
+        cls, steps = r.last_aux()
+    finally:
+        r.set_option("raymarch_mode", 0)
+    ref_cls = ref["term"].astype(np.uint8) | (np.minimum(ref["nhits"], 7) << 2).astype(np.uint8)
+    assert int(((cls & 31) != ref_cls).sum()) == 0
+    assert np.array_equal(steps, ref["steps"])
+    assert r.last_total_steps() == ref["total_steps"]
+    rep = parity_report(img, ref["final"], cls & 31, ref_cls)
+    print("strict fhd:", rep)
+    assert rep["psnr"] >= 60.0 and rep["n_gt2"] <= 2, rep
+
+
+def test_config4_fine_step_fhd_full_size_against_the_oracle():
+    """BASELINE.json configs[3] at the size it is benchmarked at: -r fhd -s 0.02 --r_max 30
+    (1.15 G RK4 steps on the CPU oracle, max_iter 60 000)."""
+    kw = dict(step_size=0.02, r_max=30.0)
+    r, sky, tex, pov, fov, W, H = _scene("fhd", **kw)
+    okw = dict(step_size=0.02, r_max=30.0, r_inner=2.0, r_outer=15.0)
+    ref = O.render(W, H, pov, fov, sky, tex, want_escape_dir=True, **okw)
+    rep, d, boundary = _check_gate_full_size(r, ref, pov, fov, max_outliers=4, max_outlier_delta=48)
+    assert abs(r.last_total_steps() - ref["total_steps"]) <= 1e-3 * ref["total_steps"]
+    assert r.last_aux()[1].mean() > 400
 
 
 def test_config3_4k_aa_tilt_flare_full_size_against_the_oracle():
@@ -194,9 +251,80 @@ def test_config3_4k_aa_tilt_flare_full_size_against_the_oracle():
     lens flare (8.3 M rays, 600 M variational RK4 steps)."""
     kw = dict(anti_alias="lod_radius", disk_tilt=20.0, lens_flare=True)
     r, sky, tex, pov, fov, W, H = _scene("4k", **kw)
-    ref = _oracle(W, H, pov, fov, sky, tex, kw)
-    rep, d, boundary = _check_gate_full_size(r, ref, pov, fov)
-    assert int((d[~boundary] > 2).sum()) <= 8, rep
+    okw = dict(step_size=0.1, r_max=10.0, r_inner=2.0, r_outer=15.0, disk_tilt=20.0, anti_alias="lod_radius")
+    ref = O.render(W, H, pov, fov, sky, tex, lens_flare_on=True, want_escape_dir=True, **okw)
+    _check_gate_full_size(r, ref, pov, fov, max_outliers=8, max_outlier_delta=48)
+
+
+def test_config5_orbit_video_frames_against_the_oracle():
+    """BASELINE.json configs[4]: orbit-video frames 0, 59, 60, 61 and 900 at fhd with the lifecycle
+    texture (416 x 2912) against an oracle run of the SAME lifecycle: host factories ticked frame
+    by frame, and for the compared frames the oracle's background / entity layer / [statistics at
+    frame % 60 == 0] / compose / mips, then the oracle's render with the orbit camera.  Covers the
+    background kernel at production size, the statistics cadence across a block boundary (59 uses
+    frame 0's statistics, 61 frame 60's) and a camera at theta != 0.  Then the same frames through
+    the real driver loop (driver.run_video_frames, the pipelined u8 path) must be bit-identical."""
+    from black_hole_renderer_b200 import Renderer
+    from black_hole_renderer_b200.driver import orbit_camera, run_video_frames
+    from black_hole_renderer_b200.lifecycle import advance_lifecycle_frame, init_lifecycle_system, make_factories
+    W, H = RESOLUTIONS["fhd"]
+    pov, fov, dt, n_total = [6.0, 0.0, 0.5], 90.0, 0.1, 3600
+    n_phi, n_r = O.disk_texture_resolution(W, H, pov, fov, 2.0, 15.0)
+    assert (n_r, n_phi) == (416, 2912)
+    sky = synthetic_skybox()
+    wanted = (0, 59, 60, 61, 900)
+    # ---- oracle side ----
+    rng = np.random.default_rng(42)
+    az_freq, az_shear = int(rng.integers(2, 5)), float(rng.uniform(2.0, 4.0))
+    F = make_factories(2.0, 15.0, n_r, n_phi, seed=42)
+    edge, omega = O.edge_alpha(n_r), O.omega_rows(n_r, 2.0, 15.0)
+    comp = np.zeros((13, n_r, n_phi), dtype=np.float32)
+    refs, stats, rows = {}, None, None
+    for frame in range(max(wanted) + 1):
+        t = frame * dt
+        for f in F.values():
+            f.tick(now=t, dt=dt)
+        if frame not in wanted:
+            continue
+        O.generate_background(comp, az_freq, az_shear, 2.0, 15.0, t)
+        comp[5:11] = O.accumulate_entities(F, t, n_r, n_phi, omega)
+        if frame % 60 == 0:
+            stats, rows = O.interactive_stats(comp, edge)
+        tex = O.compose_texture(comp, omega, edge, stats, rows)
+        cam = orbit_camera(pov, frame, n_total, 360.0)
+        refs[frame] = O.render(W, H, cam, fov, sky, tex, mips=O.build_mips(tex, 5, numpy_order=False))
+        refs[frame]["tex"] = tex
+    # ---- device side: the driver's per-frame sequence ----
+    r = Renderer(W, H, sky, np.zeros((n_r, n_phi, 4), np.float32))
+    G = init_lifecycle_system(r, n_r, n_phi, seed=42)
+    got_u8 = {}
+    for frame in range(max(wanted) + 1):
+        t = frame * dt
+        if frame in wanted:
+            advance_lifecycle_frame(r, G, t, dt, recompute_stats=(frame % 60 == 0))
+            cam = orbit_camera(pov, frame, n_total, 360.0)
+            img = r.render(cam, fov, aux=True)
+            cls, steps = r.last_aux()
+            ref = refs[frame]
+            assert np.abs(r.disk_texture_field.to_numpy() - ref["tex"]).max() <= 5e-5, frame
+            ref_cls = ref["term"].astype(np.uint8) | (np.minimum(ref["nhits"], 7) << 2).astype(np.uint8)
+            rep = parity_report(img, ref["final"], cls & 31, ref_cls)
+            print(f"orbit frame {frame}:", rep)
+            assert rep["class_flip_frac"] <= 1e-4 and rep["psnr"] >= 45.0, (frame, rep)
+            assert rep["n_gt2"] <= max(4, rep["class_flips"] + 4), (frame, rep)
+            got_u8[frame] = r.render_u8(cam, fov).copy()
+        else:
+            for f in G.values():
+                f.tick(now=t, dt=dt)
+    # ---- the same frames through the real frame loop (everything else marked completed) ----
+    frames = {}
+    r2 = Renderer(W, H, sky, np.zeros((n_r, n_phi, 4), np.float32))
+    done = set(range(n_total)) - set(wanted)
+    n = run_video_frames(r2, n_total, fov, pov, True, 360.0, dt, completed=done,
+                         sink=lambda f, img: frames.__setitem__(f, img.copy()))
+    assert n == len(wanted) and sorted(frames) == sorted(wanted)
+    for f in wanted:
+        assert np.array_equal(frames[f], got_u8[f]), f
 
 
 def test_fhd_full_size_properties():
@@ -230,8 +358,9 @@ def test_bloom_against_oracle_and_linearity():
     from black_hole_renderer_b200 import Renderer
     W, H = 640, 360
     r, sky, tex, pov, fov, W, H = _scene("sd")
+    from black_hole_renderer_b200 import _lib as L
     r.render(pov, fov)
-    disk = r.disk_layer_field.to_numpy().transpose(1, 0, 2)
+    disk = r._planar(L.BUF_DISK).transpose(1, 2, 0)            # the ray march's layer (pre-bloom)
     blur = r.blur_field.to_numpy().transpose(1, 0, 2)
     want = O.bloom(disk, W)
     assert np.abs(blur - want).max() < 2e-6
@@ -271,17 +400,49 @@ def test_strict_div6_is_the_ieee_division_on_every_float():
     assert total.value < 2 * 6 * 2 ** 23 + 16
 
 
-def test_render_to_field_layout():
-    """render_to_field (render.py:3819-3863): final_field is (W, H, 3), y-flipped, without flare."""
-    r, sky, tex, pov, fov, W, H = _scene((160, 90), lens_flare=True)
-    r.lens_flare = False
-    want = r.render(pov, fov)
-    r.lens_flare = True
+@pytest.mark.parametrize("name", ["raymarch_default", "raymarch_aa_tilt_flare"])
+def test_render_to_field_matches_reference_golden(name):
+    """render_to_field (render.py:3819-3863) against the reference's own final_field
+    (tests/golden/render_to_field.npz, produced by the unmodified reference through the shim):
+    final = clamp(bg + clamp(disk + 0.4 blur) + blur), (W, H, 3), y-flipped, never flared -- and
+    the disk layer field is left post-bloom, after render() as well (render.py:3112-3114)."""
+    d = np.load(os.path.join(GOLDEN, name + ".npz"))
+    g = np.load(os.path.join(GOLDEN, "render_to_field.npz"))
+    r, pov, fov = _renderer_for(d, "strict")                   # (lens_flare on in the second case)
+    W, H = r.width, r.height
     r.render_to_field(pov, fov)
     got = r.final_field.to_numpy()
     assert got.shape == (W, H, 3)
-    assert np.array_equal(got, want[::-1].transpose(1, 0, 2))
-    assert not np.array_equal(r.render(pov, fov), want)        # (the flare is on for render())
+    assert np.abs(got - g[name + "/final_field"]).max() < 2e-5
+    assert np.abs(r.disk_layer_field.to_numpy() - g[name + "/disk_layer_field"]).max() < 2e-5
+    r.render_to_field(pov, fov, skip_bloom=True)
+    assert np.abs(r.final_field.to_numpy() - g[name + "/final_field_skip_bloom"]).max() < 2e-5
+    assert np.abs(r.disk_layer_field.to_numpy() - g[name + "/disk_layer_field_skip_bloom"]).max() < 2e-5
+    # render() composites the pre-bloom layer but leaves the field post-bloom too
+    img = r.render(pov, fov)
+    assert np.abs(img - d["final"]).max() < 2e-5
+    assert np.abs(r.disk_layer_field.to_numpy().transpose(1, 0, 2) - d["disk_layer_after_bloom"]).max() < 2e-5
+    r.render(pov, fov, skip_bloom=True)
+    assert np.abs(r.disk_layer_field.to_numpy().transpose(1, 0, 2) - d["disk_layer"]).max() < 2e-5
+
+
+def test_render_to_field_against_the_oracle():
+    """The same at a size the goldens do not reach (sd, fast integrator, AA + tilt), against
+    oracle.render_to_field; the frame differs from render()'s by the 0.4 x bloom it adds."""
+    kw = dict(anti_alias="lod_radius", disk_tilt=20.0, lens_flare=True)
+    r, sky, tex, pov, fov, W, H = _scene("sd", **kw)
+    okw = dict(disk_tilt=20.0, anti_alias="lod_radius")
+    ref = O.render_to_field(W, H, pov, fov, sky, tex, **okw)
+    r.render_to_field(pov, fov)
+    got = r.final_field.to_numpy()
+    frame = got[:, ::-1].transpose(1, 0, 2)                     # back to (H, W, 3), top row first
+    rep = parity_report(frame, ref["frame"])
+    assert rep["n_gt2"] <= 2 and rep["psnr"] >= 45.0, rep
+    post = r.disk_layer_field.to_numpy()
+    assert np.abs(post - ref["disk_layer_field"]).mean() < 1e-5
+    r.lens_flare = False
+    plain = r.render(pov, fov)
+    assert np.abs(frame - plain).max() > 0.01 and (frame >= plain - 1e-6).all()
 
 
 def test_async_frames_equal_synchronous_frames():

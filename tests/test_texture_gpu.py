@@ -213,6 +213,29 @@ def test_legacy_parametric_rotation_path():
     assert not np.array_equal(got, O.compose_texture(comp, state.omega_rows, state.edge, stats, rows))
 
 
+def test_shifted_compose_against_the_reference_numpy_generator():
+    """f4: upload_parametric_state + update_disk_texture_gpu against the reference's numpy
+    _generate_disk_texture_rotating_from_state (tests/golden/shifted_compose.npz, written by
+    oracle/make_golden.py from the reference itself) at the offsets and the tolerance of the
+    reference's own test (tests/unit/test_gpu_texture_compose.py:98-112: < 1e-4)."""
+    from types import SimpleNamespace
+    g = np.load(os.path.join(GOLDEN, "shifted_compose.npz"))
+    names = ["temp_base", "spiral", "spiral_temp", "turbulence", "turb_temp", "arcs", "arcs_temp",
+             "rt_spikes", "rt_temp", "hotspot", "hotspot_temp", "az_hotspot", "disturb_mod"]
+    n_r, n_phi = int(g["n_r"][0]), int(g["n_phi"][0])
+    state = SimpleNamespace(n_r=n_r, n_phi=n_phi, enable_rt=bool(g["enable_rt"][0]), color_temp=float(g["color_temp"][0]),
+                            omega_rows=g["omega_rows"], edge=g["edge"], **{k: g["state_" + k] for k in names})
+    r = _renderer(n_r, n_phi)
+    r.upload_parametric_state(state)
+    np.testing.assert_allclose(r._comp_field.to_numpy(), np.stack([g["state_" + k] for k in names]), atol=1e-6)
+    for t in (0.0, 5.0, 50.0, 180.0):
+        r.update_disk_texture_gpu(t)
+        got = r.disk_texture_field.to_numpy()
+        assert np.abs(got - g[f"tex_t{t:g}"]).max() < 1e-4, t
+        # mip kernels against generate_disk_mipmaps on the same texture (reference test: < 1e-3)
+        assert np.abs(r.disk_mips_field.to_numpy() - O.build_mips(got, 5, numpy_order=True)).max() < 1e-6
+
+
 def test_noise_continuity_and_fbm_bound():
     """tests/unit/test_simplex_noise.py: Lipschitz continuity of the simplex noise and the bound
     sum(persistence^k) of the FBM."""

@@ -73,8 +73,10 @@ def test_resume_skips_completed_and_replays_lifecycle(tmp_path):
     r2 = FakeRenderer()
     _run(tmp_path, r2, n_frames=10, resume=True)
     assert len(r2.cams) == 5                       # frames 5..9 only
-    # replay of frames 0..4 (render.py:4427-4434) + the five new frames + init
-    assert len(r2.bg_times) == 1 + 5 + 5
+    # init + the texture pass of the block's first frame (its statistics; frame 0 itself is on disk)
+    # + the five new frames; frames 1..4 are replayed on the host only (factory ticks)
+    assert len(r2.bg_times) == 1 + 1 + 5
+    assert r2.stats_calls == 2
     # changed parameters restart from scratch
     r3 = FakeRenderer()
     _run(tmp_path, r3, n_frames=10, resume=True, degrees=180.0)
@@ -100,6 +102,43 @@ def test_static_camera_and_sharding(tmp_path):
     assert sorted(prog["completed"]) == list(range(150))
     # every rank recomputes the statistics on the first frame of each block it owns
     assert a.stats_calls == 1 + 2 and b.stats_calls == 1 + 1
+
+
+def test_sharded_resume_reads_the_per_rank_progress_files(tmp_path):
+    """An interrupted 2-rank run leaves only progress.<rank>.json behind (the merged progress.json
+    is written after the final barrier).  --resume must pick those up, render exactly the missing
+    frames with the cameras and lifecycle times of an uninterrupted run, and list a frame only when
+    its PNG exists."""
+    from black_hole_renderer_b200.driver import load_progress, render_video
+    out = str(tmp_path / "v.mp4")
+    kw = dict(n_frames=150, fps=4, output_path=out, fov=90.0, static_cam_pos=[6, 0, 0.5], orbit=True,
+              disk_rotation_speed=0.1, orbit_degrees=360.0, world_size=2)
+    full = [FakeRenderer(), FakeRenderer()]
+    for rank in (1, 0):
+        render_video(full[rank], 8, 4, rank=rank, **kw)
+    d = tmp_path / [x for x in os.listdir(tmp_path) if x.startswith(".frames_")][0]
+    # simulate the crash: no merged file; rank 0 got through frames 0..39, rank 1 through 60..99,
+    # and frame 70's PNG was never written although it is listed
+    os.remove(d / "progress.json")
+    params = json.load(open(d / "progress.0.json"))["params"]
+    json.dump({"params": params, "completed": list(range(40))}, open(d / "progress.0.json", "w"))
+    json.dump({"params": params, "completed": list(range(60, 100))}, open(d / "progress.1.json", "w"))
+    os.remove(d / "frame_0070.png")
+    done, match = load_progress(str(d), params)
+    assert match and done == set(range(40)) | (set(range(60, 100)) - {70})
+    res = [FakeRenderer(), FakeRenderer()]
+    for rank in (1, 0):
+        render_video(res[rank], 8, 4, rank=rank, resume=True, **kw)
+    want0 = [c for f, c in zip(list(range(60)) + list(range(120, 150)), full[0].cams) if f >= 40]
+    want1 = [c for f, c in zip(range(60, 120), full[1].cams) if f == 70 or f >= 100]
+    assert res[0].cams == want0 and res[1].cams == want1
+    # lifecycle times of the texture passes: each resumed block starts with its statistics frame
+    assert res[0].bg_times[1:] == [0.0] + [f * 0.1 for f in range(40, 60)] + [f * 0.1 for f in range(120, 150)]
+    assert res[1].bg_times[1:] == [6.0, 7.0] + [f * 0.1 for f in range(100, 120)]
+    assert res[0].stats_calls == 1 + 2 and res[1].stats_calls == 1 + 1
+    prog = json.load(open(d / "progress.json"))
+    assert sorted(prog["completed"]) == list(range(150))
+    assert all(os.path.isfile(d / f"frame_{f:04d}.png") for f in range(150))
 
 
 def test_encode_png_round_trips_through_pil(tmp_path):

@@ -32,7 +32,7 @@ def run(res, pov, fov, **kw):
     same = ~steps_diff & ~clsd
     print(f"{res} pov={pov} fov={fov} {kw}: bad(d>1)={int((d>1).sum())} bad(d>2)={int((d>2).sum())} clsdiff={int(clsd.sum())} stepdiff={int(steps_diff.sum())}  | same steps+class: d>1 {int((d>1)[same].sum())} d>2 {int((d>2)[same].sum())} retraced {r.last_retrace_count()}")
     if os.environ.get("DETAIL"):
-        bg = r.image_field.to_numpy().transpose(1,0,2); dk = r.disk_layer_field.to_numpy().transpose(1,0,2)
+        bg = r.image_field.to_numpy().transpose(1,0,2); dk = r._planar(1).transpose(1,2,0)
         ys_, xs_ = np.nonzero(d > 1)
         for y, x in list(zip(ys_, xs_))[:12]:
             print(f"     px ({x},{y}) d={d[y,x]} eps={eps[y,x]:.4f} cls gpu {cls[y,x]&31} ref {ref['term'][y,x] | (min(ref['nhits'][y,x],7)<<2)} steps gpu {steps[y,x]} ref {ref['steps'][y,x]} ncross {nc[y,x]}"

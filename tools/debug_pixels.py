@@ -10,7 +10,7 @@ n_phi, n_r = O.disk_texture_resolution(W, H, pov, fov, 2.0, 15.0)
 sky = synthetic_skybox(); tex = synthetic_disk_texture(n_r, n_phi)
 r = Renderer(W, H, sky, tex); r.set_option("raymarch_mode", 0)
 img = r.render(pov, fov, aux=True, skip_bloom=True); cls, steps = r.last_aux()
-bg = r.image_field.to_numpy().transpose(1,0,2); dk = r.disk_layer_field.to_numpy().transpose(1,0,2)
+bg = r.image_field.to_numpy().transpose(1,0,2); dk = r._planar(1).transpose(1,2,0)
 ref = O.render(W, H, pov, fov, sky, tex, skip_bloom=True)
 g8 = (np.clip(img,0,1)*np.float32(255)).astype(np.uint8).astype(int); r8 = (np.clip(ref['final'],0,1)*np.float32(255)).astype(np.uint8).astype(int)
 d = np.abs(g8-r8).max(-1)

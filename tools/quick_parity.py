@@ -17,7 +17,7 @@ def golden_case(name, mode):
     img = r.render(list(p[2:5]), p[5])
     print(f"  {name} mode={mode}: final max|d|={np.abs(img - d['final']).max():.3g} "
           f"bg {np.abs(r.image_field.to_numpy().transpose(1,0,2) - d['bg']).max():.3g} "
-          f"disk {np.abs(r.disk_layer_field.to_numpy().transpose(1,0,2) - d['disk_layer']).max():.3g} "
+          f"disk {np.abs(r._planar(1).transpose(1,2,0) - d['disk_layer']).max():.3g} "
           f"blur {np.abs(r.blur_field.to_numpy().transpose(1,0,2) - d['blur']).max():.3g}")
     img2 = r.render(list(p[2:5]), p[5], skip_bloom=True)
     print(f"      skip_bloom max|d|={np.abs(img2 - d['final_skip_bloom']).max():.3g}")
