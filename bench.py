@@ -149,7 +149,7 @@ def orbit_video_full(r, rank, world, dist, torch, n_frames=3600, block=60):
     if dist:
         dist.barrier()
     t0 = time.perf_counter()
-    rendered = run_video_frames(r, n_frames, FOV, POV, True, 360.0, 0.1, rank, world, factories=factories, depth=7)
+    rendered = run_video_frames(r, n_frames, FOV, POV, True, 360.0, 0.1, rank, world, factories=factories)
     torch.cuda.synchronize()
     sec = time.perf_counter() - t0
     launches = r.launch_count() - launches0
@@ -173,19 +173,18 @@ def orbit_video_full(r, rank, world, dist, torch, n_frames=3600, block=60):
 def d2h_probe(r, torch, dist, rank, world, nbytes, reps=8):
     """Raw D2H bandwidth of one frame-sized pinned copy (GB/s): every rank alone (the others idle)
     and all ranks at once.  Separates what the host fabric can take from what the renderer does."""
-    import ctypes as C
     from black_hole_renderer_b200 import _lib as L
-    dev_ptr, _ = r.device_buffer(L.BUF_FINAL)
-    host = r.pinned_frame(np.float32)
-    assert host.nbytes >= nbytes
-    cudart = torch.cuda.cudart()
+    from black_hole_renderer_b200.dist import device_tensor
+    dev = device_tensor(r, L.BUF_FINAL, (r.height, r.width, 3))
+    host = torch.empty((r.height, r.width, 3), dtype=torch.float32, pin_memory=True)
+    assert host.numel() * 4 == nbytes
     stream = torch.cuda.current_stream()
 
     def one_round():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for _ in range(reps):
-            err = cudart.cudaMemcpyAsync(host.ctypes.data, dev_ptr, nbytes, 2, stream.cuda_stream)   # 2 = cudaMemcpyDeviceToHost
+            host.copy_(dev, non_blocking=True)
         e1.record(stream)
         e1.synchronize()
         return nbytes * reps / (e0.elapsed_time(e1) * 1e-3) / 1e9

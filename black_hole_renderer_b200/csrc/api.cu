@@ -112,8 +112,8 @@ extern "C" void bhr_destroy(bhr_ctx* ctx) {
                     ctx->d_wsum_y, ctx->comp, ctx->edge, ctx->omega_rows, ctx->row_stats, ctx->d_entities, ctx->stats_scratch, ctx->stats_state, ctx->d_coltab};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int k = 0; k < 6; ++k) if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
-    for (int k = 0; k < 8; ++k) if (ctx->ent_ev[k]) cudaEventDestroy(ctx->ent_ev[k]);
-    for (int k = 0; k < 8; ++k) if (ctx->frame_ev[k]) cudaEventDestroy(ctx->frame_ev[k]);
+    for (int k = 0; k < BHR_FRAME_SLOTS; ++k) if (ctx->ent_ev[k]) cudaEventDestroy(ctx->ent_ev[k]);
+    for (int k = 0; k < BHR_FRAME_SLOTS; ++k) if (ctx->frame_ev[k]) cudaEventDestroy(ctx->frame_ev[k]);
     for (int k = 0; k < 12; ++k) if (ctx->band_ev[k]) cudaEventDestroy(ctx->band_ev[k]);
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
     if (ctx->copy_done) cudaEventDestroy(ctx->copy_done);
@@ -396,7 +396,7 @@ extern "C" int bhr_render(bhr_ctx* ctx, const bhr_camera* cam, uint32_t flags, f
 
 extern "C" int bhr_render_async(bhr_ctx* ctx, const bhr_camera* cam, uint32_t flags, float* out_f32, uint8_t* out_u8, int slot) {
     BhrDeviceGuard device_guard_(ctx);
-    if (!ctx || !cam || slot < 0 || slot >= 8) return BHR_ERR_INVALID;
+    if (!ctx || !cam || slot < 0 || slot >= BHR_FRAME_SLOTS) return BHR_ERR_INVALID;
     if (!ctx->copy_stream) BHR_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     int rc = render_enqueue(ctx, cam, flags, out_f32, out_u8, ctx->copy_stream);
     if (rc) return rc;
@@ -407,7 +407,7 @@ extern "C" int bhr_render_async(bhr_ctx* ctx, const bhr_camera* cam, uint32_t fl
 
 extern "C" int bhr_wait_frame(bhr_ctx* ctx, int slot) {
     BhrDeviceGuard device_guard_(ctx);
-    if (!ctx || slot < 0 || slot >= 8) return BHR_ERR_INVALID;
+    if (!ctx || slot < 0 || slot >= BHR_FRAME_SLOTS) return BHR_ERR_INVALID;
     if (!ctx->frame_ev[slot]) BHR_FAIL(ctx, BHR_ERR_STATE, "no frame was enqueued in slot %d", slot);
     BHR_CUDA(ctx, cudaEventSynchronize(ctx->frame_ev[slot]));
     return BHR_OK;

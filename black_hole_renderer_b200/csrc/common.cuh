@@ -9,6 +9,7 @@
 
 #define BHR_NUM_MIPS 5          // base + 4 levels, render.py:2239
 #define BHR_FLARE_BLOCKS 592     // blocks of the flare-sum reduction (4 per SM)
+#define BHR_FRAME_SLOTS 32       // frames in flight of a pipelined video loop (completion events, entity staging ring)
 #define BHR_N_COMP 13           // component planes, render.py:2328-2332
 
 // Per-frame parameters of the ray-march kernel (kernel argument, lives in constant bank 0).
@@ -90,12 +91,12 @@ struct bhr_ctx {
     float stats[2];
     int bg_ready, az_freq; float az_shear;
     bhr_entity* d_entities; int entities_cap;      // 8-slot ring: entities + slot maps (texture.cu)
-    void* h_entities; double* d_coltab; int ent_ring; cudaEvent_t ent_ev[8];
+    void* h_entities; double* d_coltab; int ent_ring; cudaEvent_t ent_ev[BHR_FRAME_SLOTS];
     float* stats_scratch;              // device statistics: density / structure planes, row results (stats.cu)
     void* stats_state;
 
     cudaEvent_t ev[6];
-    cudaEvent_t frame_ev[8];           // completion events of bhr_render_async slots
+    cudaEvent_t frame_ev[BHR_FRAME_SLOTS]; // completion events of bhr_render_async slots
     cudaStream_t copy_stream;          // D2H of finished frames (bhr_render_async), overlaps the next frame
     // peer-memory tiled frame (peer.cu)
     int peer_rank, peer_world, peer_distributed; unsigned peer_serial;

@@ -519,7 +519,7 @@ extern "C" int bhr_accumulate_entities(bhr_ctx* ctx, const bhr_entity* entities,
     if (!ctx->bg_ready) BHR_FAIL(ctx, BHR_ERR_STATE, "Must call init_background_layer() first");
     // host staging ring (pinned): the caller's array may be reused as soon as we return, and the
     // upload must not wait for the frames still in flight on the stream
-    const int n_slots_ring = 8;
+    const int n_slots_ring = BHR_FRAME_SLOTS;
     if (n > ctx->entities_cap) {
         BHR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         if (ctx->d_entities) cudaFree(ctx->d_entities);

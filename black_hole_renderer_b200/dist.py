@@ -104,21 +104,23 @@ def gather_rows(tile, height, rank, world_size, dst=0, group=None, bounds=None, 
     bounds = bounds or equal_bounds(height, world_size)
     if rank == dst:
         if out is not None:
-            reqs = [dist.irecv(out[bounds[r]:bounds[r + 1]], r, group=group) for r in range(world_size)
-                    if r != dst and bounds[r + 1] > bounds[r]]
-            for q in reqs:
+            ops = [dist.P2POp(dist.irecv, out[bounds[r]:bounds[r + 1]], r, group=group) for r in range(world_size)
+                   if r != dst and bounds[r + 1] > bounds[r]]
+            for q in dist.batch_isend_irecv(ops) if ops else ():
                 q.wait()
             return out
         parts = []
         for r in range(world_size):
             parts.append(tile if r == dst else torch.empty((bounds[r + 1] - bounds[r],) + tuple(tile.shape[1:]),
                                                            dtype=tile.dtype, device=tile.device))
-        reqs = [dist.irecv(parts[r], r, group=group) for r in range(world_size) if r != dst and parts[r].shape[0] > 0]
-        for q in reqs:
+        ops = [dist.P2POp(dist.irecv, parts[r], r, group=group) for r in range(world_size)
+               if r != dst and parts[r].shape[0] > 0]
+        for q in dist.batch_isend_irecv(ops) if ops else ():
             q.wait()
         return torch.cat(parts, dim=0)
     if tile.shape[0] > 0:
-        dist.send(tile.contiguous(), dst, group=group)
+        for q in dist.batch_isend_irecv([dist.P2POp(dist.isend, tile.contiguous(), dst, group=group)]):
+            q.wait()
     return None
 
 

@@ -22,6 +22,7 @@ from .renderer import R_DISK_INNER_DEFAULT, R_DISK_OUTER_DEFAULT, Renderer, comp
 from .skybox import load_or_generate_skybox
 
 STATS_PERIOD = 60   # frames between recompute_interactive_stats calls
+FRAME_SLOTS = 32    # completion-event slots of bhr_render_async (csrc/common.cuh: BHR_FRAME_SLOTS)
 
 
 def save_image(image, path):
@@ -153,14 +154,16 @@ def load_progress(temp_dir, params):
 
 
 def run_video_frames(renderer, n_frames, fov, static_cam_pos, orbit, orbit_degrees, dt, rank=0, world_size=1,
-                     completed=(), sink=None, on_rendered=None, ring=24, depth=5, factories=None):
+                     completed=(), sink=None, on_rendered=None, ring=None, depth=28, factories=None):
     """The frame loop of render_video (render.py:4437-4458) for the frames `rank` owns.
 
     Pipelined: frames are enqueued without waiting (texture kernels, render, D2H into one of `ring`
     pinned buffers) and the host runs up to `depth` frames ahead of the device: it does the
     lifecycle ticks / entity packing of the next frames -- and, with several ranks, the ticks of
     the frames other ranks own -- while the device works; a frame is retired (waited for, handed to
-    `sink(frame, u8_array)`) when `depth` newer ones are in flight.  `sink` may return a future: the
+    `sink(frame, u8_array)`) when `depth` newer ones are in flight.  `depth` is sized for the sharded
+    job: between two of its own 60-frame blocks a rank of an 8-GPU run ticks 420 foreign frames
+    (~30 ms of host time); 28 queued frames (~30 ms of device work) keep the GPU busy meanwhile.  `sink` may return a future: the
     buffer is not reused before it resolves.
 
     Lifecycle state: every rank ticks the factories of EVERY frame (the RNG streams are the
@@ -172,13 +175,17 @@ def run_video_frames(renderer, n_frames, fov, static_cam_pos, orbit, orbit_degre
     if factories is None:
         factories = init_lifecycle_system(renderer, renderer.dtex_h, renderer.dtex_w, seed=42)
     completed = set(completed)
+    if ring is None:                           # ~300 MB of page-locked frames: 48 at fhd, 12 at 4K
+        frame_bytes = 3 * getattr(renderer, "width", 1920) * getattr(renderer, "height", 1080)
+        ring = int(min(48, max(8, 300e6 // frame_bytes)))
+    depth = max(1, min(depth, FRAME_SLOTS - 1, ring - 4))
     bufs = [renderer.pinned_frame(np.uint8) for _ in range(ring)]
     busy = [None] * ring                       # future of the sink still reading the buffer
     in_flight = []                             # (frame, slot) enqueued, not yet waited for
 
     def retire(item):
         frame_done, slot = item
-        renderer.wait_frame(slot % 8)          # (eight completion-event slots; depth + 1 <= 8 frames in flight)
+        renderer.wait_frame(slot % FRAME_SLOTS)    # (depth + 1 <= FRAME_SLOTS frames in flight)
         if sink is not None:
             busy[slot] = sink(frame_done, bufs[slot])
 
@@ -197,7 +204,7 @@ def run_video_frames(renderer, n_frames, fov, static_cam_pos, orbit, orbit_degre
                 busy[slot].result()
                 busy[slot] = None
             advance_lifecycle_frame(renderer, factories, t, dt, recompute_stats=block_start)
-            renderer.render_u8_async(cam_pos, fov, bufs[slot], slot % 8, frame=0)
+            renderer.render_u8_async(cam_pos, fov, bufs[slot], slot % FRAME_SLOTS, frame=0)
             in_flight.append((frame, slot))
             if len(in_flight) > depth:
                 retire(in_flight.pop(0))

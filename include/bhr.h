@@ -138,7 +138,7 @@ int bhr_upload_disk_texture(bhr_ctx* ctx, const float* rgba, int n_r, int n_phi)
 int bhr_render(bhr_ctx* ctx, const bhr_camera* cam, uint32_t flags, float* out_f32, uint8_t* out_u8);
 /* The same without the final synchronisation, for pipelined video loops: the frame is enqueued
  * (ray march ... composite, copies into the PINNED host buffers) and completion event `slot`
- * (0..7) is recorded; bhr_wait_frame(slot) blocks until that frame is in host memory.  The host
+ * (0..31) is recorded; bhr_wait_frame(slot) blocks until that frame is in host memory.  The host
  * can prepare the next frame (lifecycle tick, entity packing) while the device works. */
 int bhr_render_async(bhr_ctx* ctx, const bhr_camera* cam, uint32_t flags, float* out_f32, uint8_t* out_u8, int slot);
 int bhr_wait_frame(bhr_ctx* ctx, int slot);

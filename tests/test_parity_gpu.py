@@ -209,7 +209,7 @@ def test_config2_fhd_full_size_against_the_oracle():
     c = _fhd_default_case()
     r, ref = c["r"], c["ref"]
     r.set_option("raymarch_mode", 0)
-    rep, d, boundary = _check_gate_full_size(r, ref, c["pov"], c["fov"], max_outliers=2, max_outlier_delta=48)
+    rep, d, boundary = _check_gate_full_size(r, ref, c["pov"], c["fov"], max_outliers=2, max_outlier_delta=16)
     assert r.last_total_steps() == int(r.last_aux()[1].sum())
     assert abs(r.last_total_steps() - ref["total_steps"]) <= 1e-3 * ref["total_steps"]
 
@@ -241,7 +241,7 @@ def test_config4_fine_step_fhd_full_size_against_the_oracle():
     r, sky, tex, pov, fov, W, H = _scene("fhd", **kw)
     okw = dict(step_size=0.02, r_max=30.0, r_inner=2.0, r_outer=15.0)
     ref = O.render(W, H, pov, fov, sky, tex, want_escape_dir=True, **okw)
-    rep, d, boundary = _check_gate_full_size(r, ref, pov, fov, max_outliers=4, max_outlier_delta=48)
+    rep, d, boundary = _check_gate_full_size(r, ref, pov, fov, max_outliers=2, max_outlier_delta=16)
     assert abs(r.last_total_steps() - ref["total_steps"]) <= 1e-3 * ref["total_steps"]
     assert r.last_aux()[1].mean() > 400
 
@@ -253,7 +253,7 @@ def test_config3_4k_aa_tilt_flare_full_size_against_the_oracle():
     r, sky, tex, pov, fov, W, H = _scene("4k", **kw)
     okw = dict(step_size=0.1, r_max=10.0, r_inner=2.0, r_outer=15.0, disk_tilt=20.0, anti_alias="lod_radius")
     ref = O.render(W, H, pov, fov, sky, tex, lens_flare_on=True, want_escape_dir=True, **okw)
-    _check_gate_full_size(r, ref, pov, fov, max_outliers=8, max_outlier_delta=48)
+    _check_gate_full_size(r, ref, pov, fov, max_outliers=4, max_outlier_delta=16)
 
 
 def test_config5_orbit_video_frames_against_the_oracle():
