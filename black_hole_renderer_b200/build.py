@@ -9,7 +9,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
-SOURCES = ["api.cu", "raymarch.cu", "post.cu", "texture.cu", "stats.cu", "peer.cu", "png.cu"]
+SOURCES = ["api.cu", "raymarch.cu", "post.cu", "bloom.cu", "texture.cu", "stats.cu", "peer.cu", "png.cu"]
 LIB = os.path.join(HERE, "libbhr.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default"]

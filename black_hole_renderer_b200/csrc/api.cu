@@ -92,7 +92,7 @@ extern "C" int bhr_create(const bhr_config* cfg, bhr_ctx** out) {
     for (int k = 0; k < 6; ++k) CREATE_CHECK(cudaEventCreate(&ctx->ev[k]));
     tint_6000(ctx->tint);
     ctx->stats[0] = 0.5f; ctx->stats[1] = 0.5f;    // render.py:3533
-    if (bhr_setup_bloom_tables(ctx) != BHR_OK) {
+    if (bhr_setup_bloom_tables(ctx) != BHR_OK || bhr_setup_bloom_tma(ctx) != BHR_OK) {
         snprintf(g_bhr_create_error, sizeof(g_bhr_create_error), "%s", ctx->err);
         bhr_destroy(ctx);
         return BHR_ERR_CUDA;
@@ -161,6 +161,8 @@ extern "C" int bhr_set_option(bhr_ctx* ctx, const char* key, double value) {
     if (ctx && !strcmp(key, "band_box")) { ctx->band_box = (int)value; return BHR_OK; }
     if (ctx && !strcmp(key, "strict_warps")) { ctx->strict_warps = (int)value; return BHR_OK; }
     if (ctx && !strcmp(key, "peer_timeout_ms")) { ctx->peer_timeout_ms = value; return BHR_OK; }
+    if (ctx && !strcmp(key, "bloom_generic")) { ctx->bloom_generic = (int)value; return BHR_OK; }
+    if (ctx && !strcmp(key, "keep_blur")) { ctx->keep_blur = (int)value; return BHR_OK; }
     if (ctx) snprintf(ctx->err, sizeof(ctx->err), "unknown option %s", key);
     return BHR_ERR_INVALID;
 }
@@ -441,6 +443,11 @@ extern "C" int bhr_download(bhr_ctx* ctx, int id, void* host, size_t bytes) {
     BhrDeviceGuard device_guard_(ctx);
     if (!ctx || !host) return BHR_ERR_INVALID;
     void* d; size_t n;
+    if ((id == BHR_BUF_BLUR || id == BHR_BUF_DISK_POST) && ctx->bloom_tma && !(ctx->bloom_generic & 2) && !ctx->keep_blur) {
+        // the fused V pass keeps `blur` in registers: form blur_field now from the H-blurred layer of the last frame
+        int rc = bhr_launch_blur_only(ctx);
+        if (rc) return rc;
+    }
     if (id == BHR_BUF_DISK_POST) {
         // formed on demand (an inspection path: the reference's disk_layer_field after a bloomed frame)
         n = (size_t)ctx->W * ctx->H * 12;

@@ -80,6 +80,11 @@ struct bhr_ctx {
     void* d_flare_params_own;          // device FlareParams formed from d_flare_sums (post.cu)
 
     int bloom_R; float sigma_scale;
+    // TMA bloom kernels (bloom.cu): tensor maps of the disk layer (1-row boxes, H pass) and of the H-blurred
+    // layer (64-column tiles, V pass), launch geometry; bloom_tma = 0 -> the generic kernels of post.cu
+    unsigned char tmap_disk_row[128], tmap_hblur_tile[128], tmap_bg_tile[128], tmap_disk_tile[128];
+    int bloom_tma, bloom_generic, bloom_h_P, bloom_h_bw, bloom_h_nb, bloom_h_segp, bloom_v_staged;
+    int keep_blur;                     // also write blur_field from the fused V pass (it stays in registers otherwise)
     float* d_wtab;                     // 3 x wtab_stride (2R+1 weights + zero padding)
     int wtab_stride;
     float* d_wsum_x;                   // 3 x W   1 / in-bounds weight sums (summed in sequential f32 order)
@@ -174,3 +179,8 @@ int bhr_launch_flare_sums(bhr_ctx* ctx, int row0, int row1);
 int bhr_launch_disk_post(bhr_ctx* ctx, float* out);
 int bhr_launch_build_mips(bhr_ctx* ctx, int numpy_order);
 int bhr_setup_bloom_tables(bhr_ctx* ctx);
+int bhr_setup_bloom_tma(bhr_ctx* ctx);
+int bhr_launch_bloom_h_tma(bhr_ctx* ctx, int row0, int row1);
+int bhr_launch_bloom_v_fused(bhr_ctx* ctx, uint32_t flags, int row0, int row1, const void* F_host, const void* F_dev,
+                             const float* const* row_src, float* dst_f32, uint8_t* dst_u8);
+int bhr_launch_blur_only(bhr_ctx* ctx);

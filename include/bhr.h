@@ -109,7 +109,11 @@ int bhr_version(void);
  * spreads them over more SMs -- lower latency of a small ring tile, idle warps meanwhile);
  * "stage_timing" = 1 (default): record the CUDA events bhr_last_stage_ms reads (five timing events
  * per frame, ~1.5 us of stream time each; video loops switch them off); "band_box" = 1 (default): the band-list kernel scans only the photon ring's bounding box;
- * "sync_bands" / "sync_min_bytes": row bands of synchronous host frames, see bhr_render */
+ * "sync_bands" / "sync_min_bytes": row bands of synchronous host frames, see bhr_render;
+ * "bloom_generic" = 3: use the generic bloom / composite kernels (any frame size) instead of the TMA-fed ones
+ * (widths that are a multiple of 4; same arithmetic, bit-identical frames); 1 = generic H pass only, 2 = generic
+ * V pass + composite only; "keep_blur" = 1: the fused V pass
+ * also stores blur_field (it is otherwise formed on demand by bhr_download(BHR_BUF_BLUR)) */
 int bhr_set_option(bhr_ctx* ctx, const char* key, double value);
 /* pinned host memory so that frame read-back DMA needs no staging copy */
 int bhr_host_alloc(size_t bytes, void** out);

@@ -370,6 +370,46 @@ def test_bloom_against_oracle_and_linearity():
     assert np.abs(ones - 1).max() < 1e-5
 
 
+@pytest.mark.parametrize("size,kw", [("sd", {}), ("hd", dict(lens_flare=True)), ("fhd", {}), ((644, 362), {}),
+                                     ((1924, 300), dict(lens_flare=True)), ("4k", dict(lens_flare=True, disk_tilt=20.0))])
+def test_tma_bloom_kernels_equal_the_generic_kernels(size, kw):
+    """csrc/bloom.cu (TMA-staged tiles, FFMA2 stencil, V pass fused with composite / flare / u8)
+    against the generic kernels of csrc/post.cu (option "bloom_generic"): same tap order, same
+    FMA per tap, so frames, the 8-bit frames, blur_field (formed on demand), render_to_field and
+    row-range stages (odd boundaries, tiles shorter than the radius) must be BIT-identical.
+    Sizes: P = 5 and P = 15 runs of the H pass, ragged right edges, radius 12 / 25 / 38 / 76."""
+    import ctypes as C
+    from black_hole_renderer_b200 import _lib as L
+    r, sky, tex, pov, fov, W, H = _scene(size, **kw)
+    out = {}
+    for generic in (3, 0):
+        r.set_option("bloom_generic", generic)
+        img = r.render(pov, fov).copy()
+        blur = r.blur_field.to_numpy()
+        post = r.disk_layer_field.to_numpy()
+        u8 = r.render_u8(pov, fov).copy()
+        r.render_to_field(pov, fov)
+        field = r.final_field.to_numpy()
+        # row ranges: H pass in three pieces with odd boundaries, V pass + composite in four
+        cam = r._camera(pov, fov, 0)
+        fl = L.FLARE_FROM_DEVICE if r.lens_flare else 0
+        cuts = (0, H // 3 + 1, H // 3 + 2, H)
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            L.check(r._ctx, r._lib.bhr_render_rows_stage1(r._ctx, C.byref(cam), 0, a, b))
+        if r.lens_flare:
+            L.check(r._ctx, r._lib.bhr_flare_sums_device(r._ctx, 0, H))
+        cuts2 = (0, 7, H // 2 + 3, H - 5, H)
+        for a, b in zip(cuts2[:-1], cuts2[1:]):
+            L.check(r._ctx, r._lib.bhr_render_rows_stage2(r._ctx, fl, a, b, None))
+        tiled = r._download(L.BUF_FINAL, (H, W, 3), np.float32)
+        out[generic] = (img, blur, post, u8, field, tiled)
+    names = ("frame", "blur_field", "disk_layer_field", "u8 frame", "final_field", "row-range frame")
+    for name, a, b in zip(names, out[3], out[0]):
+        assert np.array_equal(a, b), (name, float(np.abs(a.astype(np.float64) - b).max()))
+    assert np.array_equal(out[0][0], out[0][5])          # the row-range frame is the one-shot frame
+    assert out[0][1].max() > 0
+
+
 def test_update_disk_texture_and_errors():
     from black_hole_renderer_b200 import Renderer
     r, sky, tex, pov, fov, W, H = _scene((160, 90))
