@@ -9,7 +9,8 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
-SOURCES = ["api.cu", "raymarch.cu", "post.cu", "bloom.cu", "texture.cu", "stats.cu", "peer.cu", "png.cu"]
+SOURCES = ["api.cu", "raymarch.cu", "post.cu", "bloom.cu", "texture.cu", "background.cu", "stats.cu", "peer.cu", "png.cu"]
+EXTRA_FLAGS = {}          # per-file nvcc flags
 LIB = os.path.join(HERE, "libbhr.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default"]
@@ -51,7 +52,8 @@ def build(force=False, verbose=False):
         s, o = os.path.join(CSRC, src), os.path.join(OBJ, src[:-3] + ".o")
         if not force and os.path.exists(o) and os.path.getmtime(o) > max(os.path.getmtime(s), hdr_t):
             return ""
-        cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", o, s, "-ccbin", "/usr/bin/g++"]
+        cmd = [nvcc] + NVCC_FLAGS + extra + EXTRA_FLAGS.get(src, []) + (["-Xptxas", "-v"] if verbose else []) + \
+              ["-c", "-o", o, s, "-ccbin", "/usr/bin/g++"]
         res = subprocess.run(cmd, capture_output=True, text=True, env=env)
         if res.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}:\n" + res.stdout + res.stderr)

@@ -109,7 +109,7 @@ extern "C" void bhr_destroy(bhr_ctx* ctx) {
     if (ctx->own_stream) { cudaStreamSynchronize(ctx->own_stream); }
     void* ptrs[] = {ctx->sky, ctx->mips, ctx->tex_staging, ctx->bg, ctx->disk, ctx->hblur, ctx->blur, ctx->final_f32,
                     ctx->final_u8, ctx->cls, ctx->steps, ctx->d_flare_sums, ctx->d_flare_parts, ctx->d_flare_params_own, ctx->retrace_queue, ctx->d_queue_count, ctx->d_wtab, ctx->d_wsum_x,
-                    ctx->d_wsum_y, ctx->comp, ctx->edge, ctx->omega_rows, ctx->row_stats, ctx->d_entities, ctx->stats_scratch, ctx->stats_state, ctx->d_coltab};
+                    ctx->d_wsum_y, ctx->comp, ctx->bg_rows, ctx->edge, ctx->omega_rows, ctx->row_stats, ctx->d_entities, ctx->stats_scratch, ctx->stats_state, ctx->d_coltab};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int k = 0; k < 6; ++k) if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
     for (int k = 0; k < BHR_FRAME_SLOTS; ++k) if (ctx->ent_ev[k]) cudaEventDestroy(ctx->ent_ev[k]);
@@ -163,6 +163,7 @@ extern "C" int bhr_set_option(bhr_ctx* ctx, const char* key, double value) {
     if (ctx && !strcmp(key, "peer_timeout_ms")) { ctx->peer_timeout_ms = value; return BHR_OK; }
     if (ctx && !strcmp(key, "bloom_generic")) { ctx->bloom_generic = (int)value; return BHR_OK; }
     if (ctx && !strcmp(key, "keep_blur")) { ctx->keep_blur = (int)value; return BHR_OK; }
+    if (ctx && !strcmp(key, "background_scalar")) { ctx->background_scalar = (int)value; return BHR_OK; }
     if (ctx) snprintf(ctx->err, sizeof(ctx->err), "unknown option %s", key);
     return BHR_ERR_INVALID;
 }

@@ -95,6 +95,9 @@ struct bhr_ctx {
     float *edge, *omega_rows, *row_stats;
     float stats[2];
     int bg_ready, az_freq; float az_shear;
+    float* bg_rows;                    // 3 x n_r row quantities of the background kernel (omega, decay, shear)
+    int background_scalar;             // option: the one-texel-per-thread background kernel
+    int bg_blocks_per_sm;              // resident blocks of the packed background kernel (background.cu)
     bhr_entity* d_entities; int entities_cap;      // 8-slot ring: entities + slot maps (texture.cu)
     void* h_entities; double* d_coltab; int ent_ring; cudaEvent_t ent_ev[BHR_FRAME_SLOTS];
     float* stats_scratch;              // device statistics: density / structure planes, row results (stats.cu)
@@ -177,6 +180,9 @@ int bhr_launch_flare_params(bhr_ctx* ctx, const double* d_parts, int world, void
 size_t bhr_flare_params_size();
 int bhr_launch_flare_sums(bhr_ctx* ctx, int row0, int row1);
 int bhr_launch_disk_post(bhr_ctx* ctx, float* out);
+int bhr_setup_background(bhr_ctx* ctx);
+int bhr_launch_background(bhr_ctx* ctx, float t);
+int bhr_launch_noise_packed(bhr_ctx* ctx, const float* d_coords, int n, float* d_out);
 int bhr_launch_build_mips(bhr_ctx* ctx, int numpy_order);
 int bhr_setup_bloom_tables(bhr_ctx* ctx);
 int bhr_setup_bloom_tma(bhr_ctx* ctx);

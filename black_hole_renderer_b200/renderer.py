@@ -492,7 +492,7 @@ class Renderer:
         coords = _f32(coords)
         out = np.empty(coords.shape[0], dtype=np.float32)
         self._check(self._lib.bhr_eval_noise(self._ctx, _fp(coords), coords.shape[0],
-                                             0 if mode == "simplex" else 1, int(octaves),
+                                             {"simplex": 0, "fbm": 1, "simplex_packed": 2}[mode], int(octaves),
                                              float(persistence), float(lacunarity), _fp(out)))
         return out
 

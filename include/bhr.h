@@ -242,7 +242,8 @@ int bhr_set_stats(bhr_ctx* ctx, float density_p98, float struct_scale, const flo
 int bhr_upload_comp(bhr_ctx* ctx, const float* comp /* (13, n_r, n_phi) */);
 /* compose_interactive_texture (render.py:3714-3767): compose kernel + mip kernels */
 int bhr_compose_texture(bhr_ctx* ctx, float t_offset, int enable_rt, float color_temp);
-/* eval_noise (render.py:3769-3790): mode 0 simplex, 1 fbm; coords (n, 3) host -> out (n) host */
+/* eval_noise (render.py:3769-3790): mode 0 simplex, 1 fbm; coords (n, 3) host -> out (n) host.  Mode 2 (test hook):
+ * simplex through the background kernel's packed two-points-per-thread code (csrc/background.cu) */
 int bhr_eval_noise(bhr_ctx* ctx, const float* coords, int n, int mode, int octaves,
                    float persistence, float lacunarity, float* out);
 

@@ -236,6 +236,33 @@ def test_shifted_compose_against_the_reference_numpy_generator():
         assert np.abs(r.disk_mips_field.to_numpy() - O.build_mips(got, 5, numpy_order=True)).max() < 1e-6
 
 
+@pytest.mark.parametrize("n_r,n_phi", [(32, 128), (144, 976), (416, 2912)])
+def test_packed_background_kernel_equals_the_scalar_kernel(n_r, n_phi):
+    """background_kernel (two texels per thread in f32x2 lanes, floor / int conversions without the XU
+    pipe, row quantities tabulated at init) against background_scalar_kernel (one texel per thread,
+    the bit-exact-with-the-reference simplex3 that eval_noise exposes): every packed operation is
+    IEEE-rounded per lane in the same order, so all seven planes must be BIT-identical, at several
+    times and at the production texture size; and within 1e-6 of the oracle."""
+    r = _renderer(n_r, n_phi)
+    r.init_background_layer(n_r, n_phi, seed=42)
+    for t in (0.0, 0.1, 6.0, 359.9):
+        r.set_option("background_scalar", 1)
+        r.generate_background(t)
+        want = r._comp_field.to_numpy()
+        r.set_option("background_scalar", 0)
+        r._check(r._lib.bhr_upload_comp(r._ctx, np.full((13, n_r, n_phi), -7.0, np.float32).ctypes.data_as(
+            __import__("ctypes").POINTER(__import__("ctypes").c_float))))
+        r.generate_background(t)
+        got = r._comp_field.to_numpy()
+        for pl in (0, 1, 2, 3, 4, 11, 12):
+            assert np.array_equal(got[pl], want[pl]), (t, pl, float(np.abs(got[pl] - want[pl]).max()))
+        assert (got[5:11] == -7.0).all()                  # the entity planes are not touched
+    if n_r <= 144:
+        ref = np.zeros((13, n_r, n_phi), np.float32)
+        O.generate_background(ref, r._bg_az_freq, r._bg_az_shear, 2.0, 15.0, 359.9)
+        assert np.abs(ref[[0, 1, 2, 3, 4, 11, 12]] - got[[0, 1, 2, 3, 4, 11, 12]]).max() <= 1e-6
+
+
 def test_noise_continuity_and_fbm_bound():
     """tests/unit/test_simplex_noise.py: Lipschitz continuity of the simplex noise and the bound
     sum(persistence^k) of the FBM."""
