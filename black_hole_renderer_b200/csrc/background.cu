@@ -12,10 +12,8 @@
 //     reference's order, so the planes are bit-identical to the scalar kernel's;
 //   * takes work off the ALU and XU pipes: floor(v) and its integer come from one round-down magic
 //     add (add.rm: MAGIC + floor(v) exactly for |v| < 2^22; the low byte of the sum's bit pattern
-//     IS the hashed lattice index), the simplex ranking is 0/1 float algebra on three comparison
-//     results (1.0f / 0.0f) instead of predicate logic and selects, float(i + j + k) is
-//     fi + fj + fk, and a corner outside its kernel contributes max(t, 0)^4 * (g . p) = +-0 instead
-//     of a compare + select;
+//     IS the hashed lattice index), float(i + j + k) is fi + fj + fk, and a corner outside its
+//     kernel contributes max(t, 0)^4 * (g . p) = +-0 instead of a compare + select;
 //   * runs ONE copy of the noise code in a table-driven loop over the 13 noise terms (the scalar
 //     kernel inlines it 15 times, 74 KB of code: instruction-cache misses were 0.5 stall cycles per
 //     issue in the packed kernel's first form);
@@ -39,11 +37,7 @@ __device__ __forceinline__ float2 bits_f2(unsigned long long b) { return make_fl
 // rounding instead of two, although scalar operations with an explicit rounding modifier are never fused.  With
 // opaque constants an FMA is just an FMA.
 struct Consts { float2 one, minus_one, neg_zero; };
-__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
-    unsigned long long r;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(f2_bits(a)), "l"(f2_bits(b)), "l"(f2_bits(c)));
-    return bits_f2(r);
-}
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
 #define a2(a, b) fma2((a), K.one, (b))
 #define s2(a, b) fma2((b), K.minus_one, (a))
 #define m2(a, b) fma2((a), (b), K.neg_zero)
@@ -76,10 +70,14 @@ __device__ __forceinline__ void load_tables(unsigned char* smem /* 16-byte align
 // lattice indices modulo 256 (MAGIC + n has the integer pattern 0x4B400000 + n for |n| < 2^22)
 __device__ __forceinline__ void floor2(const Consts& K, const float2 v, float2& f, unsigned& bits_a, unsigned& bits_b) {
     const float MAGIC = 12582912.0f;                       // 1.5 * 2^23
-    unsigned long long r;
-    asm("fma.rm.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(f2_bits(v)), "l"(f2_bits(K.one)), "l"(f2_bits(k2(MAGIC))));   // rounded DOWN: MAGIC + floor(v)
-    bits_a = (unsigned)r; bits_b = (unsigned)(r >> 32);
-    f = s2(bits_f2(r), k2(MAGIC));
+#ifdef BHR_BG_XU_FLOOR
+    f = make_float2(floorf(v.x), floorf(v.y));             // FRND + F2I on the (idle) XU pipe instead of two FFMA2
+    bits_a = (unsigned)(int)f.x; bits_b = (unsigned)(int)f.y;
+#else
+    const float2 r = __ffma2_rd(v, K.one, k2(MAGIC));      // rounded DOWN: MAGIC + floor(v)
+    bits_a = __float_as_uint(r.x); bits_b = __float_as_uint(r.y);
+    f = s2(r, k2(MAGIC));
+#endif
 }
 
 // gradient index of one corner of one lane: perm[ii + o + perm[jj + p + pk]] (all offsets already added in)
@@ -108,37 +106,34 @@ __device__ __forceinline__ float2 simplex3x2(const Consts& K, const Tables& T, c
     floor2(K, a2(z, s), fk, ka, kb);
     const float2 t = m2(a2(a2(fi, fj), fk), k2(G3));      // float(i + j + k) * G3: the sum of three small integers is exact
     const float2 x0 = s2(x, s2(fi, t)), y0 = s2(y, s2(fj, t)), z0 = s2(z, s2(fk, t));
-    // simplex traversal order (render.py:2694-2712) from a = x0 >= y0, b = y0 >= z0, c = x0 >= z0 as 0/1 floats:
-    //   i1 = a (b or c)   j1 = (1 - a) b   k1 = 1 - i1 - j1        i2 = a or (b c)   j2 = b or (1 - a)   k2 = 2 - i2 - j2
-    // (products / sums of 0 and 1: exact in any rounding)
-    const float2 a = make_float2(ge01(x0.x, y0.x), ge01(x0.y, y0.y));
-    const float2 b = make_float2(ge01(y0.x, z0.x), ge01(y0.y, z0.y));
-    const float2 c = make_float2(ge01(x0.x, z0.x), ge01(x0.y, z0.y));
+    // simplex traversal order (render.py:2694-2712) as predicates of a = x0 >= y0, b = y0 >= z0, c = x0 >= z0, per
+    // lane, on the ALU pipe (compares, predicate logic, selects): the FMA pipe is this kernel's busiest unit
+    float2 i1, j1, k1, i2, j2, kk2;
+    int o1[2], p1[2], q1[2], o2[2], p2[2], q2[2];
+#pragma unroll
+    for (int l = 0; l < 2; ++l) {
+        const float xx = l ? x0.y : x0.x, yy = l ? y0.y : y0.x, zz = l ? z0.y : z0.x;
+        const bool a = xx >= yy, b = yy >= zz, c = xx >= zz;
+        const bool bi1 = a && (b || c), bj1 = !a && b, bk1 = !b && !(a && c);
+        const bool bi2 = a || (b && c), bj2 = b || !a, bk2 = !b || (!a && !c);
+        (l ? i1.y : i1.x) = bi1 ? 1.0f : 0.0f; (l ? j1.y : j1.x) = bj1 ? 1.0f : 0.0f; (l ? k1.y : k1.x) = bk1 ? 1.0f : 0.0f;
+        (l ? i2.y : i2.x) = bi2 ? 1.0f : 0.0f; (l ? j2.y : j2.x) = bj2 ? 1.0f : 0.0f; (l ? kk2.y : kk2.x) = bk2 ? 1.0f : 0.0f;
+        o1[l] = bi1; p1[l] = bj1; q1[l] = bk1; o2[l] = bi2; p2[l] = bj2; q2[l] = bk2;
+    }
     const float2 one = k2(1.0f);
-    const float2 na = s2(one, a), bc = m2(b, c);
-    const float2 i1 = m2(a, s2(a2(b, c), bc));            // a (b + c - bc)
-    const float2 j1 = m2(na, b);
-    const float2 k1 = s2(s2(one, i1), j1);
-    const float2 i2 = s2(a2(a, bc), m2(a, bc));           // a + bc - a bc
-    const float2 j2 = s2(a2(b, na), m2(b, na));           // b + (1 - a) - b (1 - a)
-    const float2 kk2 = s2(s2(k2(2.0f), i2), j2);
     const float2 x1 = a2(s2(x0, i1), k2(G3)), y1 = a2(s2(y0, j1), k2(G3)), z1 = a2(s2(z0, k1), k2(G3));
     const float2 x2 = a2(s2(x0, i2), k2(G3x2)), y2 = a2(s2(y0, j2), k2(G3x2)), z2 = a2(s2(z0, kk2), k2(G3x2));
     const float2 x3 = a2(s2(x0, one), k2(G3x3)), y3 = a2(s2(y0, one), k2(G3x3)), z3 = a2(s2(z0, one), k2(G3x3));
-    // hashing, per lane.  0/1 floats -> integers: 1.0f = 0x3F800000, so bits >> 29 is the value
+    // hashing, per lane
     int g0a, g1a, g2a, g3a, g0b, g1b, g2b, g3b;
 #pragma unroll
     for (int l = 0; l < 2; ++l) {
         const unsigned bi = l ? ib : ia, bj = l ? jb : ja, bk = l ? kb : ka;
         const int ii = bi & 255, jj = bj & 255, kk = bk & 255;
-        const int pk0 = T.t[kk], pk1 = T.t[kk + 1], dpk = pk1 - pk0;
-        const float f_i1 = l ? i1.y : i1.x, f_j1 = l ? j1.y : j1.x, f_k1 = l ? k1.y : k1.x;
-        const float f_i2 = l ? i2.y : i2.x, f_j2 = l ? j2.y : j2.x, f_k2 = l ? kk2.y : kk2.x;
-        const int o1 = __float_as_int(f_i1) >> 29, p1 = __float_as_int(f_j1) >> 29, q1 = __float_as_int(f_k1) >> 29;
-        const int o2 = __float_as_int(f_i2) >> 29, p2 = __float_as_int(f_j2) >> 29, q2 = __float_as_int(f_k2) >> 29;
+        const int pk0 = T.t[kk], pk1 = T.t[kk + 1];
         const int c0 = corner_index(T, ii, jj, pk0);
-        const int c1 = corner_index(T, ii + o1, jj + p1, pk0 + q1 * dpk);
-        const int c2 = corner_index(T, ii + o2, jj + p2, pk0 + q2 * dpk);
+        const int c1 = corner_index(T, ii + o1[l], jj + p1[l], q1[l] ? pk1 : pk0);
+        const int c2 = corner_index(T, ii + o2[l], jj + p2[l], q2[l] ? pk1 : pk0);
         const int c3 = corner_index(T, ii + 1, jj + 1, pk1);
         if (l) { g0b = c0; g1b = c1; g2b = c2; g3b = c3; } else { g0a = c0; g1a = c1; g2a = c2; g3a = c3; }
     }
@@ -185,7 +180,10 @@ __global__ void background_rows_kernel(float* __restrict__ rows, int n_r, float 
 // A thread owns two neighbouring texels of a row; blocks are persistent and walk the texel pairs grid-stride.
 // The cos / sin of the Keplerian-rotated angle feed noise coordinates scaled by up to 800, so they are evaluated
 // in double and rounded once (the oracle's ideal-libm convention).
-__global__ void __launch_bounds__(256) background_kernel(float* __restrict__ comp, const float* __restrict__ rows, int n_r, int n_phi,
+#ifndef BHR_BG_MINBLOCKS
+#define BHR_BG_MINBLOCKS 2
+#endif
+__global__ void __launch_bounds__(256, BHR_BG_MINBLOCKS) background_kernel(float* __restrict__ comp, const float* __restrict__ rows, int n_r, int n_phi,
                                                          int az_freq, float t, const Consts K) {
     __shared__ __align__(16) unsigned char stab[kTableBytes];
     Tables T;
