@@ -149,19 +149,23 @@ def orbit_video_full(r, rank, world, dist, torch, n_frames=3600, block=60):
     if dist:
         dist.barrier()
     t0 = time.perf_counter()
-    rendered = run_video_frames(r, n_frames, FOV, POV, True, 360.0, 0.1, rank, world, factories=factories)
+    timing = {}
+    rendered = run_video_frames(r, n_frames, FOV, POV, True, 360.0, 0.1, rank, world, factories=factories, timing=timing)
     torch.cuda.synchronize()
     sec = time.perf_counter() - t0
     launches = r.launch_count() - launches0
     assert rendered == per_rank[rank], (rendered, per_rank)
-    tt = torch.tensor([sec, setup_s], dtype=torch.float64, device="cuda")
+    tt = torch.tensor([sec, setup_s, timing["host_foreign_ticks_s"], timing["host_own_frames_s"],
+                       timing["host_blocked_on_device_s"]], dtype=torch.float64, device="cuda")
     if dist:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    sec, setup_s = (float(v) for v in tt.tolist())
+    sec, setup_s, h_tick, h_own, h_wait = (float(v) for v in tt.tolist())
     return {"frames": n_frames, "frames_per_s": n_frames / sec, "seconds_max_over_ranks": sec,
             "per_rank_frames": per_rank, "ms_per_frame_per_gpu": 1e3 * sec / max(per_rank),
             "balance_ceiling": n_frames / (world * max(per_rank)),
             "setup_seconds": setup_s, "frames_per_s_including_setup": n_frames / (sec + setup_s),
+            "host_seconds_max_over_ranks": {"foreign_ticks": h_tick, "own_frames_texture_pass_and_render_calls": h_own,
+                                            "blocked_on_device": h_wait},
             "gpu_launches_rank0": launches,
             "includes": "the whole 3600-frame job of render.py --video --orbit -r fhd: host lifecycle ticks of all frames on every "
                         "rank; for a rank's own frames background + entity + compose + mips kernels, statistics on each block's "

@@ -154,7 +154,7 @@ def load_progress(temp_dir, params):
 
 
 def run_video_frames(renderer, n_frames, fov, static_cam_pos, orbit, orbit_degrees, dt, rank=0, world_size=1,
-                     completed=(), sink=None, on_rendered=None, ring=None, depth=28, factories=None):
+                     completed=(), sink=None, on_rendered=None, ring=None, depth=28, factories=None, timing=None):
     """The frame loop of render_video (render.py:4437-4458) for the frames `rank` owns.
 
     Pipelined: frames are enqueued without waiting (texture kernels, render, D2H into one of `ring`
@@ -171,7 +171,11 @@ def run_video_frames(renderer, n_frames, fov, static_cam_pos, orbit, orbit_degre
     which frame 60 b fixes for block b.  A block that still has frames to render therefore starts
     with the full texture pass + statistics of its first frame even when that frame is already done
     (resume), so resumed frames equal those of an uninterrupted run.
+    `timing`: a dict that receives the host-side seconds spent in foreign ticks, in the texture pass + render
+    calls of own frames, and blocked on the device (frame retirement, buffer reuse).
     Returns the number of frames rendered."""
+    clock = time.perf_counter
+    t_tick = t_own = t_wait = 0.0
     if factories is None:
         factories = init_lifecycle_system(renderer, renderer.dtex_h, renderer.dtex_w, seed=42)
     completed = set(completed)
@@ -184,8 +188,11 @@ def run_video_frames(renderer, n_frames, fov, static_cam_pos, orbit, orbit_degre
     in_flight = []                             # (frame, slot) enqueued, not yet waited for
 
     def retire(item):
+        nonlocal t_wait
         frame_done, slot = item
+        t0 = clock()
         renderer.wait_frame(slot % FRAME_SLOTS)    # (depth + 1 <= FRAME_SLOTS frames in flight)
+        t_wait += clock() - t0
         if sink is not None:
             busy[slot] = sink(frame_done, bufs[slot])
 
@@ -201,10 +208,14 @@ def run_video_frames(renderer, n_frames, fov, static_cam_pos, orbit, orbit_degre
             cam_pos = orbit_camera(static_cam_pos, frame, n_frames, orbit_degrees) if orbit else static_cam_pos
             slot = rendered % ring
             if busy[slot] is not None:
+                t0 = clock()
                 busy[slot].result()
+                t_wait += clock() - t0
                 busy[slot] = None
+            t0 = clock()
             advance_lifecycle_frame(renderer, factories, t, dt, recompute_stats=block_start)
             renderer.render_u8_async(cam_pos, fov, bufs[slot], slot % FRAME_SLOTS, frame=0)
+            t_own += clock() - t0
             in_flight.append((frame, slot))
             if len(in_flight) > depth:
                 retire(in_flight.pop(0))
@@ -215,13 +226,17 @@ def run_video_frames(renderer, n_frames, fov, static_cam_pos, orbit, orbit_degre
             # resumed block: its first frame is on disk already, but its statistics are needed
             advance_lifecycle_frame(renderer, factories, t, dt, recompute_stats=True)
         else:
+            t0 = clock()
             for f in factories.values():      # keep the RNG streams in step; no device work
                 f.tick(now=t, dt=dt)
+            t_tick += clock() - t0
     for item in in_flight:
         retire(item)
     for b in busy:
         if b is not None:
             b.result()
+    if timing is not None:
+        timing.update(host_foreign_ticks_s=t_tick, host_own_frames_s=t_own, host_blocked_on_device_s=t_wait)
     return rendered
 
 

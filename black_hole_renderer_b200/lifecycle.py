@@ -228,6 +228,7 @@ class EntityFactory:
         self._version = 0          # bumped whenever the population changes (SoA cache key)
         self._soa = None
         self._cull = None          # column cache of the filament cull: [list identity, birth, s0, alpha, tau]
+        self._sm = None            # static-column matrix of the packer, kept in step with the list: [list identity, m, birth]
         self.entity_type = entity_type
         if entity_type not in _DRAW:
             raise ValueError(f"unknown entity_type {entity_type!r}")
@@ -266,8 +267,11 @@ class EntityFactory:
         if self.entity_type == "filament":
             self._cull_filaments(now)
         else:
-            self.entities = [e for e in self.entities
-                             if now - e.birth_time < e.fade_in + e.lifetime + e.fade_out]
+            keep = [now - e.birth_time < e.fade_in + e.lifetime + e.fade_out for e in self.entities]
+            if not all(keep):
+                old = self.entities
+                self.entities = [e for e, k in zip(old, keep) if k]
+                self._sm_cull(old, np.array(keep, dtype=bool))
         if len(self.entities) != before:
             self._version += 1
         deficit = self.target_count - len(self.entities)
@@ -280,6 +284,7 @@ class EntityFactory:
         for _ in range(n_spawn):
             e = self._spawn_one(now)
             self.entities.append(e)
+            self._sm_append(e)
             if self.entity_type == "filament":
                 self._cull_append(e)
         if n_spawn:
@@ -321,6 +326,23 @@ class EntityFactory:
             keep = ~dead
             self.entities = [e for e, k in zip(ents, keep) if k]
             self._cull = [self.entities, birth[keep], s0[keep], alpha[keep], neg_inv_tau[keep]]
+            self._sm_cull(ents, keep)
+
+    # the packer's static columns (lifecycle._factory_soa), updated in place of a rebuild from the Python objects
+    def _sm_cull(self, old_list, keep):
+        c = self._sm
+        if c is not None and c[0] is old_list and len(c[1]) == len(old_list):
+            self._sm = [self.entities, c[1][keep], c[2][keep]]
+        else:
+            self._sm = None
+
+    def _sm_append(self, e):
+        c = self._sm
+        if c is not None and c[0] is self.entities and len(c[1]) == len(self.entities) - 1:
+            c[1] = np.concatenate([c[1], np.array([_static_row(e)], dtype=np.float64)])
+            c[2] = np.append(c[2], e.birth_time)
+        else:
+            self._sm = None
 
     def _cull_append(self, e):
         c = self._cull
@@ -405,27 +427,63 @@ ENTITY_DTYPE = np.dtype([("kind", "<i4"), ("row_begin", "<i4"), ("row_end", "<i4
 assert ENTITY_DTYPE.itemsize == 96
 
 
+_FIL_COLS = ("source_phi", "alpha_shear", "tau_cool", "blob_base_r", "blob_sigma_r", "blob_sigma_phi0",
+             "blob_peak_density", "blob_peak_temp")
+_OTHER_PARAMS = {"hotspot": ("phi0", "r0", "phi_width", "r_width", "intensity"),
+                 "rt_spike": ("phi0", "r0", "phi_width", "r_length", "intensity", "delta_T")}
+
+
+def _static_row(e):
+    """The columns of an entity that never change after its birth (cached on the instance): rows, and the
+    filament's blob parameters or the hotspot's / spike's envelope + profile parameters."""
+    row = e.__dict__.get("_static")
+    if row is None:
+        if e.entity_type == "filament":
+            row = (float(e.q["rows"][0]), float(e.q["rows"][1])) + tuple(float(getattr(e, k)) for k in _FIL_COLS)
+        else:
+            row = (float(e.q["rows"][0]), float(e.q["rows"][1]), float(e.fade_in), float(e.lifetime), float(e.fade_out)) + \
+                  tuple(float(e.q[k]) for k in _OTHER_PARAMS[e.entity_type])
+        e._static = row
+    return row
+
+
 def _factory_soa(f, n_r):
-    """Static per-entity columns of a factory, rebuilt only when its population changes."""
+    """Static per-entity columns of a factory + the packed-entity template with every static field filled in,
+    rebuilt only when its population changes (one C-level conversion of the cached per-entity rows).  The template
+    is the bhr_entity array seen as 12 float64 slots per entity: slot 0 = (kind, row_begin) and slot 1 =
+    (row_end, pad) as int32 pairs, slot 2 = age, slot 3 = scale, slots 4..11 = p[0..7]."""
     key = (f._version, len(f.entities), n_r)
     if f._soa is not None and f._soa[0] == key:
         return f._soa[1]
     ents = f.entities
     n = len(ents)
-    col = dict(birth=np.array([e.birth_time for e in ents], dtype=np.float64).reshape(n),
-               r0=np.array([max(int(e.q["rows"][0]), 0) for e in ents], dtype=np.int32).reshape(n),
-               r1=np.array([min(int(e.q["rows"][1]), n_r) for e in ents], dtype=np.int32).reshape(n))
-    if f.entity_type == "filament":
-        for name in ("source_phi", "alpha_shear", "tau_cool", "blob_base_r", "blob_sigma_r",
-                     "blob_sigma_phi0", "blob_peak_density", "blob_peak_temp"):
-            col[name] = np.array([getattr(e, name) for e in ents], dtype=np.float64).reshape(n)
+    sm = getattr(f, "_sm", None)
+    if sm is not None and sm[0] is ents and len(sm[1]) == n and len(sm[2]) == n:
+        m, birth = sm[1], sm[2]               # kept in step by the factory's tick (no pass over the Python objects)
     else:
-        names = (("phi0", "r0", "phi_width", "r_width", "intensity") if f.entity_type == "hotspot"
-                 else ("phi0", "r0", "phi_width", "r_length", "intensity", "delta_T"))
-        col["params"] = np.array([[e.q[k] for k in names] for e in ents], dtype=np.float64).reshape(n, len(names))
-        col["fade_in"] = np.array([e.fade_in for e in ents], dtype=np.float64).reshape(n)
-        col["life"] = np.array([e.lifetime for e in ents], dtype=np.float64).reshape(n)
-        col["fade_out"] = np.array([e.fade_out for e in ents], dtype=np.float64).reshape(n)
+        m = np.array([_static_row(e) for e in ents], dtype=np.float64).reshape(n, -1)
+        birth = np.fromiter((e.birth_time for e in ents), dtype=np.float64, count=n)
+        f._sm = [ents, m, birth]
+    tmpl = np.zeros((n, 12), dtype=np.float64)
+    ti = tmpl.view(np.int32)                     # (n, 24)
+    ti[:, 1] = np.maximum(m[:, 0].astype(np.int32), 0)
+    ti[:, 2] = np.minimum(m[:, 1].astype(np.int32), n_r)
+    col = dict(birth=birth, tmpl=tmpl)
+    if f.entity_type == "filament":
+        for k, name in enumerate(_FIL_COLS):
+            col[name] = np.ascontiguousarray(m[:, 2 + k])
+        sigma_r = np.maximum(col["blob_sigma_r"], 1e-6)
+        col["s0"] = np.maximum(col["blob_sigma_phi0"], 1e-6)
+        col["tau_safe"] = np.where(col["tau_cool"] > 0, col["tau_cool"], 1.0)
+        col["no_tau"] = None if (col["tau_cool"] > 0).all() else ~(col["tau_cool"] > 0)
+        ti[:, 0] = 0
+        tmpl[:, 4] = col["source_phi"]
+        tmpl[:, 5] = col["blob_base_r"]
+        tmpl[:, 6] = 0.5 / (sigma_r * sigma_r)
+    else:
+        col["fade_in"], col["life"], col["fade_out"] = (np.ascontiguousarray(m[:, 2 + k]) for k in range(3))
+        ti[:, 0] = KIND[f.entity_type]
+        tmpl[:, 4:4 + m.shape[1] - 5] = m[:, 5:]
     f._soa = (key, col)
     return col
 
@@ -440,22 +498,20 @@ def pack_entities_array(factories, now, n_r):
             continue
         c = _factory_soa(f, n_r)
         age = now - c["birth"]
+        out = c["tmpl"].copy()
         if f.entity_type == "filament":
-            s0 = np.maximum(c["blob_sigma_phi0"], 1e-6)
+            s0 = c["s0"]
             sigma_t = s0 + c["alpha_shear"] * age
-            cool = np.where(c["tau_cool"] > 0, np.exp(-age / np.where(c["tau_cool"] > 0, c["tau_cool"], 1.0)), 1.0)
-            alive = (s0 / sigma_t) * cool >= FILAMENT_DEATH_THRESHOLD
+            cool = np.exp(-age / c["tau_safe"])
+            if c["no_tau"] is not None:
+                cool[c["no_tau"]] = 1.0
+            shear = s0 / sigma_t
+            alive = shear * cool >= FILAMENT_DEATH_THRESHOLD
             birth = np.minimum(age / FILAMENT_BIRTH_FADE_DUR, 1.0)
-            sigma_r = np.maximum(c["blob_sigma_r"], 1e-6)
-            out = np.zeros(len(age), dtype=ENTITY_DTYPE)
-            out["kind"] = 0
-            out["scale"] = birth * cool
-            out["p"][:, 0] = c["source_phi"]
-            out["p"][:, 1] = c["blob_base_r"]
-            out["p"][:, 2] = 0.5 / (sigma_r * sigma_r)
-            out["p"][:, 3] = 0.5 / (sigma_t * sigma_t)
-            out["p"][:, 4] = c["blob_peak_density"] * s0 / sigma_t * birth * cool
-            out["p"][:, 5] = c["blob_peak_temp"] * s0 / sigma_t * birth * cool
+            out[:, 3] = birth * cool
+            out[:, 7] = 0.5 / (sigma_t * sigma_t)
+            out[:, 8] = c["blob_peak_density"] * s0 / sigma_t * birth * cool
+            out[:, 9] = c["blob_peak_temp"] * s0 / sigma_t * birth * cool
         else:
             fin, life, fout = c["fade_in"], c["life"], c["fade_out"]
             rest = age - fin
@@ -465,15 +521,12 @@ def pack_entities_array(factories, now, n_r):
             alpha = np.where(age < 0, 0.0, np.where(age < fin, ramp_in, np.where(
                 rest < life, 1.0, np.where(rest - life < fout, ramp_out, 0.0))))
             alive = alpha > 0
-            out = np.zeros(len(age), dtype=ENTITY_DTYPE)
-            out["kind"] = KIND[f.entity_type]
-            out["scale"] = alpha
-            out["p"][:, :c["params"].shape[1]] = c["params"]
-        out["row_begin"], out["row_end"], out["age"] = c["r0"], c["r1"], age
-        parts.append(out[alive])
+            out[:, 3] = alpha
+        out[:, 2] = age
+        parts.append(out if alive.all() else out[alive])
     if not parts:
         return np.zeros(0, dtype=ENTITY_DTYPE)
-    return np.ascontiguousarray(np.concatenate(parts))
+    return np.ascontiguousarray(np.concatenate(parts)).view(ENTITY_DTYPE).reshape(-1)
 
 
 def init_lifecycle_system(renderer, n_r, n_phi, seed=42):
