@@ -136,12 +136,13 @@ def orbit_video_full(r, rank, world, dist, torch, n_frames=3600, block=60):
     [statistics on a block's first frame] + compose + mips + ray march + bloom + composite and
     copies the 8-bit frame to pinned host memory.  PNG / x264 encoding off (host I/O).  Timed from
     a barrier to the moment the slowest rank has its last frame in host memory."""
-    from black_hole_renderer_b200.driver import frame_owner, run_video_frames
+    from black_hole_renderer_b200.driver import frame_owner, run_video_frames, video_ring
     per_rank = [sum(1 for f in range(n_frames) if frame_owner(f, world, block) == k) for k in range(world)]
     r.set_option("stage_timing", 0)
     t_setup = time.perf_counter()
     from black_hole_renderer_b200.lifecycle import init_lifecycle_system
     factories = init_lifecycle_system(r, r.dtex_h, r.dtex_w, seed=42)
+    video_ring(r, 48)                      # the page-locked frame ring (one-off, ~0.3 s)
     r.synchronize()
     setup_s = time.perf_counter() - t_setup
     launches0 = r.launch_count()

@@ -78,11 +78,13 @@ SIGNATURES = {
     "bhr_download": (C.c_int, [_P, C.c_int, _P, C.c_size_t]),
     "bhr_last_total_steps": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     "bhr_launch_count": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
+    "bhr_last_raymarch_timeline": (C.c_int, [_P, C.POINTER(C.c_uint64), C.c_int]),
     "bhr_last_retrace_count": (C.c_int, [_P, C.POINTER(C.c_uint32)]),
     "bhr_last_stage_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "bhr_init_background": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_float, _FP, _FP]),
     "bhr_generate_background": (C.c_int, [_P, C.c_float]),
     "bhr_accumulate_entities": (C.c_int, [_P, C.POINTER(BhrEntity), C.c_int]),
+    "bhr_upload_entity_tables": (C.c_int, [_P, _FP, C.c_size_t]),
     "bhr_set_stats": (C.c_int, [_P, C.c_float, C.c_float, _FP]),
     "bhr_upload_comp": (C.c_int, [_P, _FP]),
     "bhr_compose_texture": (C.c_int, [_P, C.c_float, C.c_int, C.c_float]),

@@ -108,8 +108,8 @@ extern "C" void bhr_destroy(bhr_ctx* ctx) {
     if (ctx->peer_sync_own) cudaFree(ctx->peer_sync_own);
     if (ctx->own_stream) { cudaStreamSynchronize(ctx->own_stream); }
     void* ptrs[] = {ctx->sky, ctx->mips, ctx->tex_staging, ctx->bg, ctx->disk, ctx->hblur, ctx->blur, ctx->final_f32,
-                    ctx->final_u8, ctx->cls, ctx->steps, ctx->d_flare_sums, ctx->d_flare_parts, ctx->d_flare_params_own, ctx->retrace_queue, ctx->d_queue_count, ctx->d_wtab, ctx->d_wsum_x,
-                    ctx->d_wsum_y, ctx->comp, ctx->bg_rows, ctx->edge, ctx->omega_rows, ctx->row_stats, ctx->d_entities, ctx->stats_scratch, ctx->stats_state, ctx->d_coltab};
+                    ctx->final_u8, ctx->cls, ctx->steps, ctx->d_flare_sums, ctx->d_flare_parts, ctx->d_flare_params_own, ctx->d_timeline, ctx->retrace_queue, ctx->d_queue_count, ctx->d_wtab, ctx->d_wsum_x,
+                    ctx->d_wsum_y, ctx->comp, ctx->bg_rows, ctx->edge, ctx->omega_rows, ctx->row_stats, ctx->d_entity_tables, ctx->d_entities, ctx->stats_scratch, ctx->stats_state, ctx->d_coltab};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int k = 0; k < 6; ++k) if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
     for (int k = 0; k < BHR_FRAME_SLOTS; ++k) if (ctx->ent_ev[k]) cudaEventDestroy(ctx->ent_ev[k]);
@@ -163,6 +163,7 @@ extern "C" int bhr_set_option(bhr_ctx* ctx, const char* key, double value) {
     if (ctx && !strcmp(key, "peer_timeout_ms")) { ctx->peer_timeout_ms = value; return BHR_OK; }
     if (ctx && !strcmp(key, "bloom_generic")) { ctx->bloom_generic = (int)value; return BHR_OK; }
     if (ctx && !strcmp(key, "keep_blur")) { ctx->keep_blur = (int)value; return BHR_OK; }
+    if (ctx && !strcmp(key, "timeline")) { ctx->timeline = (int)value; return BHR_OK; }
     if (ctx && !strcmp(key, "background_scalar")) { ctx->background_scalar = (int)value; return BHR_OK; }
     if (ctx) snprintf(ctx->err, sizeof(ctx->err), "unknown option %s", key);
     return BHR_ERR_INVALID;
@@ -505,6 +506,16 @@ extern "C" int bhr_row_costs(bhr_ctx* ctx, int row0, int row1, uint64_t* out) {
     cudaFree(d);
     BHR_CUDA(ctx, e);
     return BHR_OK;
+}
+
+extern "C" int bhr_last_raymarch_timeline(bhr_ctx* ctx, uint64_t* out, int max_blocks) {
+    BhrDeviceGuard device_guard_(ctx);
+    if (!ctx || !out || !ctx->d_timeline) return 0;
+    const int n = max_blocks < ctx->num_sms ? max_blocks : ctx->num_sms;
+    if (cudaMemcpyAsync(out, ctx->d_timeline, (size_t)3 * n * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+        cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+        return 0;
+    return n;
 }
 
 extern "C" int bhr_launch_count(bhr_ctx* ctx, uint64_t* out) {

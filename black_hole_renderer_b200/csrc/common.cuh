@@ -54,6 +54,7 @@ struct RayParams {
     int band_prequeued;
     int band_x0, band_x1, band_y0, band_y1;   // pixels band_list_kernel scans (the ring's bounding box)
     int strict_warps;           // warps per strict block that trace band batches (the rest wait, then join the fast pool)
+    unsigned long long* timeline;   // optional (option "timeline"): per block {start, strict role done, end} in globaltimer ns
 };
 
 struct PeerSync;
@@ -99,6 +100,7 @@ struct bhr_ctx {
     int background_scalar;             // option: the one-texel-per-thread background kernel
     int bg_blocks_per_sm;              // resident blocks of the packed background kernel (background.cu)
     bhr_entity* d_entities; int entities_cap;      // 8-slot ring: entities + slot maps (texture.cu)
+    float* d_entity_tables; size_t entity_tables_cap, entity_tables_n;   // tabulated profiles of caller-owned entities (kind 3 / 4)
     void* h_entities; double* d_coltab; int ent_ring; cudaEvent_t ent_ev[BHR_FRAME_SLOTS];
     float* stats_scratch;              // device statistics: density / structure planes, row results (stats.cu)
     void* stats_state;
@@ -120,6 +122,7 @@ struct bhr_ctx {
     // completion event per band, and "this launch continues a frame: keep the RK4 step total"
     int sync_bands; double sync_min_bytes, sync_extend; cudaEvent_t band_ev[12]; int keep_step_total;
     int strict_warps, band_box, planar, planar_attr_set;
+    int timeline; unsigned long long* d_timeline;   // option "timeline": per-block timestamps of the persistent ray march
     unsigned long long launches;       // kernels this context has launched (bhr_launch_count)
     int stage_timing;                  // record the per-stage timing events (instrumentation; each costs ~1.5 us of stream time)
     cudaEvent_t frame_done;            // orders the copy stream behind the composite (no timing)

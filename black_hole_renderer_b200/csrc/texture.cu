@@ -146,6 +146,7 @@ __global__ void __launch_bounds__(256) entity_coltab_kernel(const bhr_entity* __
 struct RowEntity {
     double a, b, c;          // filament: scale_d * r_w, scale_t * r_w, 1 / (2 sigma_phi^2); others: r_prof, intensity, -
     const double* col;       // hotspot / rt_spike: azimuthal profile table
+    const float *tab_d, *tab_t;   // kind 3 / 4: this row of the caller's tabulated density / temperature profiles
     float ctr;               // filament: blob centre (float32, render.py:3633); others: fade alpha
     float tfac;              // rt_spike: delta_T
     int kind, shift;
@@ -157,7 +158,8 @@ __global__ void __launch_bounds__(256) entity_accumulate_kernel(float* __restric
                                                                 const bhr_entity* __restrict__ ents, int n_ent,
                                                                 const float* __restrict__ omega_rows,
                                                                 const int* __restrict__ ent_slot,
-                                                                const double* __restrict__ coltab) {
+                                                                const double* __restrict__ coltab,
+                                                                const float* __restrict__ tables) {
     extern __shared__ __align__(16) unsigned char ent_smem[];
     RowEntity* list = reinterpret_cast<RowEntity*>(ent_smem);
     __shared__ int warp_count[8];
@@ -185,7 +187,16 @@ __global__ void __launch_bounds__(256) entity_accumulate_kernel(float* __restric
             RowEntity R;
             R.kind = E.kind; R.col = nullptr; R.shift = 0; R.tfac = 0.0f; R.c = 0.0;
             const double rd = r_norm - E.p[1];
-            if (E.kind == 0) {
+            R.tab_d = R.tab_t = nullptr;
+            if (E.kind >= 3) {
+                // a reference EntityInstance with tabulated (rows, n_phi) float32 profiles (render.py:3640-3649):
+                // p[0] = offset of its density rows in `tables`, its temperature rows follow them
+                const size_t rows = (size_t)(E.row_end - E.row_begin);
+                R.tab_d = tables + (size_t)E.p[0] + (size_t)(ri - E.row_begin) * n_phi;
+                R.tab_t = R.tab_d + rows * n_phi;
+                R.shift = (int)__fmul_rn(__fdiv_rn(__fmul_rn((float)E.age, om), 6.2831855f), (float)n_phi);
+                R.ctr = (float)E.scale;
+            } else if (E.kind == 0) {
                 const double r_w = exp(-(rd * rd) * E.p[2]);
                 R.a = E.p[4] * r_w; R.b = E.p[5] * r_w; R.c = E.p[3];
                 // center = (source_phi - omega[ri] * age) % 2pi evaluates in float32 in the reference
@@ -229,6 +240,13 @@ __global__ void __launch_bounds__(256) entity_accumulate_kernel(float* __restric
                 const double prof = exp(-d_phi * d_phi * R.c);
                 acc[0] = (float)((double)acc[0] + prof * R.a);
                 acc[1] = (float)((double)acc[1] + prof * R.b);
+            } else if (R.kind >= 3) {
+                // staging[d, ri] += np.roll(phi_density[k], -shift) * alpha: float32 product, float32 sum
+                int src = (pi + R.shift) % n_phi;
+                if (src < 0) src += n_phi;
+                const int d = R.kind == 3 ? 4 : 2;              // hotspot -> comp[9], comp[10]; rt_spike -> comp[7], comp[8]
+                acc[d] = __fadd_rn(acc[d], __fmul_rn(R.tab_d[src], R.ctr));
+                acc[d + 1] = __fadd_rn(acc[d + 1], __fmul_rn(R.tab_t[src], R.ctr));
             } else {
                 int src = (pi + R.shift) % n_phi;
                 if (src < 0) src += n_phi;
@@ -434,6 +452,16 @@ extern "C" int bhr_accumulate_entities(bhr_ctx* ctx, const bhr_entity* entities,
             if (!ctx->ent_ev[k]) BHR_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ent_ev[k], cudaEventDisableTiming));
         ctx->ent_ring = 0;
     }
+    for (int e = 0; e < n; ++e) {
+        const bhr_entity& E = entities[e];
+        if (E.kind < 0 || E.kind > 4 || E.row_begin < 0 || E.row_end > ctx->n_r || E.row_begin > E.row_end)
+            BHR_FAIL(ctx, BHR_ERR_INVALID, "entity %d: bad kind / row range", e);
+        if (E.kind >= 3) {
+            const double need = E.p[0] + 2.0 * (double)(E.row_end - E.row_begin) * ctx->n_phi;
+            if (E.p[0] < 0 || need > (double)ctx->entity_tables_n)
+                BHR_FAIL(ctx, BHR_ERR_INVALID, "entity %d references profile tables that were not uploaded (bhr_upload_entity_tables)", e);
+        }
+    }
     const size_t plane = (size_t)ctx->n_r * ctx->n_phi;
     if (n == 0) {
         BHR_CUDA(ctx, cudaMemsetAsync(ctx->comp + 5 * plane, 0, 6 * plane * sizeof(float), ctx->stream));
@@ -451,7 +479,7 @@ extern "C" int bhr_accumulate_entities(bhr_ctx* ctx, const bhr_entity* entities,
     memcpy(h_ent, entities, (size_t)n * sizeof(bhr_entity));
     int n_tab = 0;
     for (int e = 0; e < n; ++e) {
-        if (entities[e].kind != 0) { h_slot[e] = n_tab; h_slot_ent[n_tab++] = e; } else h_slot[e] = -1;
+        if (entities[e].kind == 1 || entities[e].kind == 2) { h_slot[e] = n_tab; h_slot_ent[n_tab++] = e; } else h_slot[e] = -1;
     }
     BHR_CUDA(ctx, cudaMemcpyAsync(d, h, per, cudaMemcpyHostToDevice, ctx->stream));
     const bhr_entity* d_ent = (const bhr_entity*)d;
@@ -469,10 +497,28 @@ extern "C" int bhr_accumulate_entities(bhr_ctx* ctx, const bhr_entity* entities,
         BHR_CUDA(ctx, cudaFuncSetAttribute(entity_accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(bhr_div_up(ctx->n_phi, kEntCols), ctx->n_r);
     entity_accumulate_kernel<<<grid, 256, smem, ctx->stream>>>(ctx->comp, ctx->n_r, ctx->n_phi, d_ent, n, ctx->omega_rows,
-                                                               d_slot, coltab);
+                                                               d_slot, coltab, ctx->d_entity_tables);
     ++ctx->launches;
     BHR_CUDA(ctx, cudaGetLastError());
     BHR_CUDA(ctx, cudaEventRecord(ctx->ent_ev[ring], ctx->stream));
+    return BHR_OK;
+}
+
+// Tabulated profiles of caller-owned entities (the reference's EntityInstance.phi_density / phi_temp): one float32
+// buffer, referenced by kind 3 / 4 entities through p[0].  Replaces the previous upload.
+extern "C" int bhr_upload_entity_tables(bhr_ctx* ctx, const float* data, size_t n_floats) {
+    BhrDeviceGuard device_guard_(ctx);
+    if (!ctx || (n_floats > 0 && !data)) return BHR_ERR_INVALID;
+    BHR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));           // kernels of earlier frames may still read the old buffer
+    if (n_floats > ctx->entity_tables_cap) {
+        if (ctx->d_entity_tables) cudaFree(ctx->d_entity_tables);
+        ctx->d_entity_tables = nullptr;
+        ctx->entity_tables_cap = n_floats + n_floats / 2;
+        BHR_CUDA(ctx, cudaMalloc(&ctx->d_entity_tables, ctx->entity_tables_cap * sizeof(float)));
+    }
+    if (n_floats) BHR_CUDA(ctx, cudaMemcpyAsync(ctx->d_entity_tables, data, n_floats * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    BHR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->entity_tables_n = n_floats;
     return BHR_OK;
 }
 

@@ -153,6 +153,19 @@ def load_progress(temp_dir, params):
     return completed, match
 
 
+def video_ring(renderer, ring):
+    """The renderer's ring of page-locked 8-bit frames, allocated once (page-locking a 6 MB frame takes ~6 ms:
+    48 of them cost more than rendering 250 frames) and reused by every later video loop of that renderer."""
+    cache = getattr(renderer, "_video_ring", None)
+    if cache is None or len(cache) < ring:
+        cache = list(cache or []) + [renderer.pinned_frame(np.uint8) for _ in range(ring - len(cache or []))]
+        try:
+            renderer._video_ring = cache
+        except AttributeError:
+            pass
+    return cache[:ring]
+
+
 def run_video_frames(renderer, n_frames, fov, static_cam_pos, orbit, orbit_degrees, dt, rank=0, world_size=1,
                      completed=(), sink=None, on_rendered=None, ring=None, depth=28, factories=None, timing=None):
     """The frame loop of render_video (render.py:4437-4458) for the frames `rank` owns.
@@ -183,7 +196,7 @@ def run_video_frames(renderer, n_frames, fov, static_cam_pos, orbit, orbit_degre
         frame_bytes = 3 * getattr(renderer, "width", 1920) * getattr(renderer, "height", 1080)
         ring = int(min(48, max(8, 300e6 // frame_bytes)))
     depth = max(1, min(depth, FRAME_SLOTS - 1, ring - 4))
-    bufs = [renderer.pinned_frame(np.uint8) for _ in range(ring)]
+    bufs = video_ring(renderer, ring)
     busy = [None] * ring                       # future of the sink still reading the buffer
     in_flight = []                             # (frame, slot) enqueued, not yet waited for
 

@@ -529,6 +529,82 @@ def pack_entities_array(factories, now, n_r):
     return np.ascontiguousarray(np.concatenate(parts)).view(ENTITY_DTYPE).reshape(-1)
 
 
+def _row_runs(row_indices, n_r):
+    """Contiguous [begin, end) runs of an entity's row_indices clipped to the texture, with the index of each run's
+    first row in the entity's profile arrays."""
+    rows = np.asarray(row_indices, dtype=np.int64)
+    runs, k = [], 0
+    while k < len(rows):
+        j = k
+        while j + 1 < len(rows) and rows[j + 1] == rows[j] + 1:
+            j += 1
+        a, b = int(rows[k]), int(rows[j]) + 1
+        lo, hi = max(a, 0), min(b, n_r)
+        if lo < hi:
+            runs.append((lo, hi, k + (lo - a)))
+        k = j + 1
+    return runs
+
+
+def pack_foreign_entities(factories, now, n_r, n_phi, table_cache):
+    """bhr_entity array for factories whose entities are NOT this module's EntityInstance -- e.g. the reference's
+    own EntityFactory / EntityInstance objects (render.py:499-792), which carry tabulated (rows, n_phi) float32
+    profiles instead of analytic parameters.  Filaments are analytic in the reference too (render.py:3605-3636)
+    and are packed from their attributes; hotspots and RT spikes become kind 3 / 4 entries that reference their
+    phi_density / phi_temp rows in one float32 table buffer.  `table_cache`: dict kept by the renderer; returns
+    (entities, tables or None): tables is the new buffer to upload when the set of tabulated entities changed."""
+    ents = []
+    tabulated = []
+    for key in ("filament", "rt_spike", "hotspot"):
+        f = factories.get(key)
+        if f is None:
+            continue
+        for e in f.alive_entities:
+            age = now - e.birth_time
+            if e.entity_type == "filament":
+                if e.density_factor(age) < FILAMENT_DEATH_THRESHOLD:
+                    continue
+                s0 = max(e.blob_sigma_phi0, 1e-6)
+                sigma_t = s0 + e.alpha_shear * age
+                birth = min(age / FILAMENT_BIRTH_FADE_DUR, 1.0) if FILAMENT_BIRTH_FADE_DUR > 0 else 1.0
+                cool = math.exp(-age / e.tau_cool) if e.tau_cool > 0 else 1.0
+                sigma_r = max(e.blob_sigma_r, 1e-6)
+                vals = [e.source_phi, e.blob_base_r, 0.5 / (sigma_r * sigma_r), 0.5 / (sigma_t * sigma_t),
+                        e.blob_peak_density * s0 / sigma_t * birth * cool, e.blob_peak_temp * s0 / sigma_t * birth * cool]
+                for lo, hi, _ in _row_runs(e.row_indices, n_r):
+                    ents.append((0, lo, hi, age, birth * cool, vals))
+            else:
+                alpha = e.fade_factor(now)
+                if alpha <= 0:
+                    continue
+                tabulated.append((e, 3 if key == "hotspot" else 4, age, alpha))
+    # table buffer: rebuilt (and re-uploaded) only when the set of tabulated entities changes.  Every contiguous run
+    # of an entity's rows inside the texture gets its density rows followed by its temperature rows.
+    ids = tuple(id(e) for e, _, _, _ in tabulated)
+    tables = None
+    if table_cache.get("ids") != ids:
+        chunks, runs_of, off = [], {}, 0
+        for e, _, _, _ in tabulated:
+            d = np.ascontiguousarray(e.phi_density, dtype=np.float32).reshape(-1, n_phi)
+            t = np.ascontiguousarray(e.phi_temp, dtype=np.float32).reshape(-1, n_phi)
+            mine = []
+            for lo, hi, k0 in _row_runs(e.row_indices, n_r):
+                mine.append((lo, hi, off))
+                chunks += [d[k0:k0 + hi - lo].ravel(), t[k0:k0 + hi - lo].ravel()]
+                off += 2 * (hi - lo) * n_phi
+            runs_of[id(e)] = mine
+        tables = np.concatenate(chunks) if chunks else np.zeros(0, dtype=np.float32)
+        table_cache.update(ids=ids, runs=runs_of, keep=[e for e, _, _, _ in tabulated])   # (keep: ids stay unique while cached)
+    for e, kind, age, alpha in tabulated:
+        for lo, hi, off in table_cache["runs"][id(e)]:
+            ents.append((kind, lo, hi, age, alpha, [float(off)]))
+    out = np.zeros(len(ents), dtype=ENTITY_DTYPE)
+    for i, (kind, lo, hi, age, scale, vals) in enumerate(ents):
+        out[i]["kind"], out[i]["row_begin"], out[i]["row_end"], out[i]["age"], out[i]["scale"] = kind, lo, hi, age, scale
+        out[i]["p"][:len(vals)] = vals
+    return out, tables
+
+
 def init_lifecycle_system(renderer, n_r, n_phi, seed=42):
     """_init_lifecycle_system (render.py:4079-4130): background parameters, three factories
     (seeds +100/+200/+300, targets 200/30/15), staggered initial population, first texture."""

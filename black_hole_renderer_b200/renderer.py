@@ -383,9 +383,16 @@ class Renderer:
 
     def accumulate_entity_layer(self, factories, now):
         """Sum every alive entity into comp[5:11] on the device (render.py:3564-3653)."""
-        from .lifecycle import pack_entities_array
+        from .lifecycle import EntityFactory, pack_entities_array, pack_foreign_entities
         assert self._bg_ready, "Must call init_background_layer() first"
-        ents = pack_entities_array(factories, now, self._bg_n_r)
+        if all(isinstance(f, EntityFactory) for f in factories.values() if f is not None):
+            ents = pack_entities_array(factories, now, self._bg_n_r)
+        else:
+            # the caller's own factory objects (e.g. the reference's EntityFactory with tabulated profiles)
+            cache = self.__dict__.setdefault("_foreign_tables", {})
+            ents, tables = pack_foreign_entities(factories, now, self._bg_n_r, self._bg_n_phi, cache)
+            if tables is not None:
+                self._check(self._lib.bhr_upload_entity_tables(self._ctx, _fp(tables) if len(tables) else None, len(tables)))
         ptr = ents.ctypes.data_as(C.POINTER(L.BhrEntity)) if len(ents) else None
         self._check(self._lib.bhr_accumulate_entities(self._ctx, ptr, len(ents)))
 

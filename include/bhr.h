@@ -197,6 +197,10 @@ int bhr_last_total_steps(bhr_ctx* ctx, uint64_t* out);
 /* kernels of this library launched by the context since bhr_create (render path, texture pipeline,
  * peer flags; the statistics / test hooks are not counted) -- what bench.py reports as gpu_launches */
 int bhr_launch_count(bhr_ctx* ctx, uint64_t* out);
+/* Instrumentation (option "timeline" = 1): {start, strict role done, end} of every block of the last persistent
+ * ray-march launch in nanoseconds of the GPU's global timer, 3 x min(max_blocks, SMs) values.  Returns the number of
+ * blocks written (0: nothing recorded / failure) -- a count, not a bhr_status. */
+int bhr_last_raymarch_timeline(bhr_ctx* ctx, uint64_t* out, int max_blocks);
 /* number of rays the last ray march re-traced with the exactly-rounded integrator */
 int bhr_last_retrace_count(bhr_ctx* ctx, uint32_t* out);
 /* device time (ms, CUDA events) of the stages of the last bhr_render: {ray march, bloom H,
@@ -215,7 +219,11 @@ int bhr_generate_background(bhr_ctx* ctx, float t);
 /* One entity of the lifecycle system as the accumulate kernel consumes it
  * (accumulate_entity_layer, render.py:3564-3653).  kind 0 = filament (Gaussian blob sheared by
  * differential rotation), 1 = hotspot, 2 = rt_spike (analytic profiles of
- * _spawn_single_hotspot / _spawn_single_rt_spike, render.py:1725-1866, rolled per row). */
+ * _spawn_single_hotspot / _spawn_single_rt_spike, render.py:1725-1866, rolled per row);
+ * kind 3 = hotspot, 4 = rt_spike given as the reference's own tabulated float32 profiles
+ * (EntityInstance.phi_density / phi_temp, (rows, n_phi) each, uploaded with bhr_upload_entity_tables):
+ * p[0] = offset (in floats) of the entity's density rows in that buffer, its temperature rows follow;
+ * scale = fade alpha; the kernel does numpy's float32 `+= roll(row, -shift) * alpha`. */
 typedef struct {
     int32_t kind;
     int32_t row_begin, row_end;   /* affected rows [row_begin, row_end)        */
@@ -224,6 +232,7 @@ typedef struct {
     double p[8];                  /* kind-specific parameters, see texture.cu  */
 } bhr_entity;
 int bhr_accumulate_entities(bhr_ctx* ctx, const bhr_entity* entities, int n);
+int bhr_upload_entity_tables(bhr_ctx* ctx, const float* data, size_t n_floats);
 /* recompute_interactive_stats (render.py:3655-3712) on the device.  The reference runs
  * np.percentile / np.quantile on the host; here the device returns the exact order statistics next
  * to each quantile's virtual index and the caller applies numpy's interpolation to them:

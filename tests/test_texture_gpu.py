@@ -263,6 +263,48 @@ def test_packed_background_kernel_equals_the_scalar_kernel(n_r, n_phi):
         assert np.abs(ref[[0, 1, 2, 3, 4, 11, 12]] - got[[0, 1, 2, 3, 4, 11, 12]]).max() <= 1e-6
 
 
+def test_reference_style_entity_objects_are_accepted():
+    """Drop-in boundary: accumulate_entity_layer takes the CALLER'S factory objects -- the reference's EntityFactory /
+    EntityInstance (render.py:499-792) carry tabulated phi_density / phi_temp / row_indices arrays, not this package's
+    analytic parameters.  Duck-typed copies of such objects (plain namespaces with the reference dataclass's fields and
+    methods) go through the tabulated-profile kernel path, which does numpy's float32 `+= roll(row, -shift) * alpha`:
+    hotspot / RT-spike planes bit-equal to the reference's numpy loop (oracle.accumulate_entities), filaments <= 1e-6."""
+    from types import SimpleNamespace
+    from black_hole_renderer_b200 import lifecycle as LC
+    n_r, n_phi = 64, 256
+    r = _renderer(n_r, n_phi)
+    r.init_background_layer(n_r, n_phi, seed=42)
+    own = LC.make_factories(2.0, 15.0, n_r, n_phi, seed=42)
+    for frame in range(40):
+        for f in own.values():
+            f.tick(now=frame * 0.1, dt=0.1)
+    now = 3.9
+
+    def foreign(e):
+        ns = SimpleNamespace(entity_type=e.entity_type, birth_time=e.birth_time, lifetime=e.lifetime, fade_in=e.fade_in,
+                             fade_out=e.fade_out, omega=e.omega, row_indices=np.array(e.row_indices),
+                             source_phi=e.source_phi, alpha_shear=e.alpha_shear, tau_cool=e.tau_cool,
+                             blob_base_r=e.blob_base_r, blob_sigma_r=e.blob_sigma_r, blob_sigma_phi0=e.blob_sigma_phi0,
+                             blob_peak_density=e.blob_peak_density, blob_peak_temp=e.blob_peak_temp,
+                             phi_density=np.array(e.phi_density) if e.entity_type != "filament" else np.zeros((0, 0), np.float32),
+                             phi_temp=np.array(e.phi_temp) if e.entity_type != "filament" else np.zeros((0, 0), np.float32))
+        ns.density_factor = e.density_factor
+        ns.fade_factor = e.fade_factor
+        return ns
+
+    theirs = {k: SimpleNamespace(alive_entities=[foreign(e) for e in f.alive_entities]) for k, f in own.items()}
+    want = O.accumulate_entities(theirs, now, n_r, n_phi, r._bg_omega_all_np)
+    for _ in range(2):                                   # second call: the table cache is reused
+        r.accumulate_entity_layer(theirs, now)
+        got = r._comp_field.to_numpy()[5:11]
+        assert np.array_equal(got[2:6], want[2:6])       # rt_spike (7, 8) and hotspot (9, 10) planes: bit-equal
+        assert np.abs(got[0:2] - want[0:2]).max() <= 1e-6
+    assert want[2:6].max() > 0 and want[0:2].max() > 0
+    # ... and the package's own factories still take the analytic path, to the same planes within float32 noise
+    r.accumulate_entity_layer(own, now)
+    assert np.abs(r._comp_field.to_numpy()[5:11] - want).max() <= 2e-6
+
+
 def test_noise_continuity_and_fbm_bound():
     """tests/unit/test_simplex_noise.py: Lipschitz continuity of the simplex noise and the bound
     sum(persistence^k) of the FBM."""
