@@ -128,21 +128,23 @@ def lifecycle_texture_cpu(n_r, n_phi, r_inner=2.0, r_outer=15.0):
     return tex
 
 
-def orbit_video_full(r, rank, world, dist, torch, n_frames=3600, block=60):
+def orbit_video_full(r, rank, world, dist, torch, n_frames=3600, block=60, png=False):
     """BASELINE.json configs[4] as a whole job: `render.py --video --orbit --n_frames 3600 --fps 36
     -r fhd` through the CLI's own frame loop (driver.run_video_frames, render.py:4437-4458): frames
     dealt to ranks in 60-frame blocks (the statistics cadence), every rank replays the host
     lifecycle ticks of ALL frames and, for its own frames, runs background + entity layer +
     [statistics on a block's first frame] + compose + mips + ray march + bloom + composite and
     copies the 8-bit frame to pinned host memory.  PNG / x264 encoding off (host I/O).  Timed from
-    a barrier to the moment the slowest rank has its last frame in host memory."""
-    from black_hole_renderer_b200.driver import frame_owner, run_video_frames, video_ring
+    a barrier to the moment the slowest rank has its last frame in host memory.
+    png=True: the frames leave the device as the deflate streams of their PNG files (csrc/png.cu) -- what the CLI
+    writes to disk after adding the chunk framing; the D2H per frame shrinks to the stream's length."""
+    from black_hole_renderer_b200.driver import frame_owner, png_ring, run_video_frames, video_ring
     per_rank = [sum(1 for f in range(n_frames) if frame_owner(f, world, block) == k) for k in range(world)]
     r.set_option("stage_timing", 0)
     t_setup = time.perf_counter()
     from black_hole_renderer_b200.lifecycle import init_lifecycle_system
     factories = init_lifecycle_system(r, r.dtex_h, r.dtex_w, seed=42)
-    video_ring(r, 48)                      # the page-locked frame ring (one-off, ~0.3 s)
+    (png_ring if png else video_ring)(r, 48)      # the page-locked frame ring (one-off, ~0.3 s)
     r.synchronize()
     setup_s = time.perf_counter() - t_setup
     launches0 = r.launch_count()
@@ -151,7 +153,8 @@ def orbit_video_full(r, rank, world, dist, torch, n_frames=3600, block=60):
         dist.barrier()
     t0 = time.perf_counter()
     timing = {}
-    rendered = run_video_frames(r, n_frames, FOV, POV, True, 360.0, 0.1, rank, world, factories=factories, timing=timing)
+    rendered = run_video_frames(r, n_frames, FOV, POV, True, 360.0, 0.1, rank, world, factories=factories, timing=timing,
+                                png=png)
     torch.cuda.synchronize()
     sec = time.perf_counter() - t0
     launches = r.launch_count() - launches0
@@ -161,6 +164,20 @@ def orbit_video_full(r, rank, world, dist, torch, n_frames=3600, block=60):
     if dist:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     sec, setup_s, h_tick, h_own, h_wait = (float(v) for v in tt.tolist())
+    if png:
+        nb = torch.tensor([float(timing["png_stream_bytes"])], dtype=torch.float64, device="cuda")
+        if dist:
+            dist.all_reduce(nb)
+        return {"frames": n_frames, "frames_per_s": n_frames / sec, "seconds_max_over_ranks": sec,
+                "ms_per_frame_per_gpu": 1e3 * sec / max(per_rank),
+                "mean_stream_bytes_per_frame": float(nb.item()) / n_frames, "raw_bytes_per_frame": 3 * r.width * r.height,
+                "host_seconds_max_over_ranks": {"foreign_ticks": h_tick, "own_frames_texture_pass_and_render_calls": h_own,
+                                                "blocked_on_device": h_wait},
+                "gpu_launches_rank0": launches,
+                "includes": "the orbit_video_full job with each frame Sub-filtered, run-length matched and Huffman coded ON THE "
+                            "DEVICE (3 kernels after the composite); the host receives each frame's complete zlib stream "
+                            "(copy sized from the previous frames' streams)",
+                "excludes": "CRC-32 + file write + x264 mux (host I/O)"}
     return {"frames": n_frames, "frames_per_s": n_frames / sec, "seconds_max_over_ranks": sec,
             "per_rank_frames": per_rank, "ms_per_frame_per_gpu": 1e3 * sec / max(per_rank),
             "balance_ceiling": n_frames / (world * max(per_rank)),
@@ -566,9 +583,10 @@ def main():
     d2h = d2h_probe(r, torch, dist if world > 1 else None, rank, world, W * H * 12)
 
     # ---- orbit video (BASELINE.json configs[4]): the whole 3600-frame job ----
-    orbit = None
+    orbit = orbit_png = None
     if not args.no_orbit:
         orbit = orbit_video_full(r, rank, world, dist if world > 1 else None, torch, n_frames=args.orbit_frames)
+        orbit_png = orbit_video_full(r, rank, world, dist if world > 1 else None, torch, n_frames=args.orbit_frames, png=True)
     clocks = sampler.stop() if sampler else None      # sampled every 20 ms over all the timed regions above
 
     # ---- the other BASELINE.json configurations, device-resident, rank 0 at N = 1 (parity-tested in
@@ -635,6 +653,8 @@ def main():
     }
     if orbit:
         line["orbit_video_full"] = orbit
+        if orbit_png is not None:
+            line["orbit_video_device_png"] = orbit_png
     if other:
         line["other_configs"] = other
     if tiled:

@@ -69,6 +69,12 @@ SIGNATURES = {
     "bhr_row_costs": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_uint64)]),
     "bhr_render_async": (C.c_int, [_P, C.POINTER(BhrCamera), C.c_uint32, _P, _P, C.c_int]),
     "bhr_wait_frame": (C.c_int, [_P, C.c_int]),
+    "bhr_png_setup": (C.c_int, [_P, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
+                                C.POINTER(C.c_uint32), C.POINTER(C.c_uint8), C.c_uint32, C.c_uint32, C.c_uint32]),
+    "bhr_png_capacity": (C.c_int, [_P, C.POINTER(C.c_size_t)]),
+    "bhr_render_async_png": (C.c_int, [_P, C.POINTER(BhrCamera), C.c_uint32, _P, C.c_size_t, C.c_int]),
+    "bhr_png_fetch": (C.c_int, [_P, C.c_int, C.c_size_t, C.c_size_t, _P]),
+    "bhr_png_encode_current": (C.c_int, [_P, _P, C.c_size_t, C.POINTER(C.c_uint32)]),
     "bhr_render_rows_stage1": (C.c_int, [_P, C.POINTER(BhrCamera), C.c_uint32, C.c_int, C.c_int]),
     "bhr_render_rows_stage2": (C.c_int, [_P, C.c_uint32, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "bhr_flare_sums": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_double)]),

@@ -111,6 +111,9 @@ extern "C" void bhr_destroy(bhr_ctx* ctx) {
                     ctx->final_u8, ctx->cls, ctx->steps, ctx->d_flare_sums, ctx->d_flare_parts, ctx->d_flare_params_own, ctx->d_timeline, ctx->retrace_queue, ctx->d_queue_count, ctx->d_wtab, ctx->d_wsum_x,
                     ctx->d_wsum_y, ctx->comp, ctx->bg_rows, ctx->edge, ctx->omega_rows, ctx->row_stats, ctx->d_entity_tables, ctx->d_entities, ctx->stats_scratch, ctx->stats_state, ctx->d_coltab};
     for (void* p : ptrs) if (p) cudaFree(p);
+    void* png[] = {ctx->d_png_tables, ctx->d_png_staging, ctx->d_png_seg, ctx->d_png_off};
+    for (void* p : png) if (p) cudaFree(p);
+    for (int k = 0; k < BHR_FRAME_SLOTS; ++k) if (ctx->d_png_stream[k]) cudaFree(ctx->d_png_stream[k]);
     for (int k = 0; k < 6; ++k) if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
     for (int k = 0; k < BHR_FRAME_SLOTS; ++k) if (ctx->ent_ev[k]) cudaEventDestroy(ctx->ent_ev[k]);
     for (int k = 0; k < BHR_FRAME_SLOTS; ++k) if (ctx->frame_ev[k]) cudaEventDestroy(ctx->frame_ev[k]);
@@ -406,6 +409,52 @@ extern "C" int bhr_render_async(bhr_ctx* ctx, const bhr_camera* cam, uint32_t fl
     if (rc) return rc;
     if (!ctx->frame_ev[slot]) BHR_CUDA(ctx, cudaEventCreateWithFlags(&ctx->frame_ev[slot], cudaEventDisableTiming));
     BHR_CUDA(ctx, cudaEventRecord(ctx->frame_ev[slot], (out_f32 || out_u8) ? ctx->copy_stream : ctx->stream));
+    return BHR_OK;
+}
+
+// A frame whose 8-bit image leaves the device as the zlib stream of its PNG file (png.cu).  host receives
+// {uint32 stream_bytes, uint32 adler32} followed by the first copy_bytes of the stream; a caller that guessed
+// copy_bytes too small (stream_bytes > copy_bytes) fetches the rest with bhr_png_fetch before it reuses the slot.
+extern "C" int bhr_render_async_png(bhr_ctx* ctx, const bhr_camera* cam, uint32_t flags, void* host, size_t copy_bytes, int slot) {
+    BhrDeviceGuard device_guard_(ctx);
+    if (!ctx || !cam || !host || slot < 0 || slot >= BHR_FRAME_SLOTS) return BHR_ERR_INVALID;
+    if (!ctx->copy_stream) BHR_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    int rc = render_enqueue(ctx, cam, flags, nullptr, nullptr, nullptr);
+    if (rc) return rc;
+    rc = bhr_launch_png_encode(ctx, slot);
+    if (rc) return rc;
+    if (copy_bytes > ctx->png_capacity) copy_bytes = ctx->png_capacity;
+    if (!ctx->frame_done) BHR_CUDA(ctx, cudaEventCreateWithFlags(&ctx->frame_done, cudaEventDisableTiming));
+    BHR_CUDA(ctx, cudaEventRecord(ctx->frame_done, ctx->stream));
+    BHR_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->frame_done, 0));
+    BHR_CUDA(ctx, cudaMemcpyAsync(host, ctx->d_png_stream[slot], 8 + copy_bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    if (!ctx->frame_ev[slot]) BHR_CUDA(ctx, cudaEventCreateWithFlags(&ctx->frame_ev[slot], cudaEventDisableTiming));
+    BHR_CUDA(ctx, cudaEventRecord(ctx->frame_ev[slot], ctx->copy_stream));
+    return BHR_OK;
+}
+
+// bytes [offset, offset + bytes) of slot's stream, synchronously (the slot's frame must have been waited for)
+extern "C" int bhr_png_fetch(bhr_ctx* ctx, int slot, size_t offset, size_t bytes, void* host) {
+    BhrDeviceGuard device_guard_(ctx);
+    if (!ctx || !host || slot < 0 || slot >= BHR_FRAME_SLOTS) return BHR_ERR_INVALID;
+    if (!ctx->d_png_stream[slot]) BHR_FAIL(ctx, BHR_ERR_STATE, "no PNG stream was encoded in slot %d", slot);
+    if (offset + bytes > ctx->png_capacity) BHR_FAIL(ctx, BHR_ERR_INVALID, "range past the stream buffer");
+    BHR_CUDA(ctx, cudaMemcpy(host, ctx->d_png_stream[slot] + 8 + offset, bytes, cudaMemcpyDeviceToHost));
+    return BHR_OK;
+}
+
+// the stream of the frame currently in BHR_BUF_FINAL_U8 (after a bhr_render), synchronously: tests and one-off files
+extern "C" int bhr_png_encode_current(bhr_ctx* ctx, void* host, size_t host_bytes, uint32_t* stream_bytes) {
+    BhrDeviceGuard device_guard_(ctx);
+    if (!ctx || !host || !stream_bytes) return BHR_ERR_INVALID;
+    int rc = bhr_launch_png_encode(ctx, 0);
+    if (rc) return rc;
+    uint32_t info[2];
+    BHR_CUDA(ctx, cudaMemcpyAsync(info, ctx->d_png_stream[0], 8, cudaMemcpyDeviceToHost, ctx->stream));
+    BHR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *stream_bytes = info[0];
+    if (info[0] > host_bytes) BHR_FAIL(ctx, BHR_ERR_INVALID, "stream of %u bytes does not fit the buffer", info[0]);
+    BHR_CUDA(ctx, cudaMemcpy(host, ctx->d_png_stream[0] + 8, info[0], cudaMemcpyDeviceToHost));
     return BHR_OK;
 }
 

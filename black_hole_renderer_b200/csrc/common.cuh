@@ -126,6 +126,9 @@ struct bhr_ctx {
     unsigned long long launches;       // kernels this context has launched (bhr_launch_count)
     int stage_timing;                  // record the per-stage timing events (instrumentation; each costs ~1.5 us of stream time)
     cudaEvent_t frame_done;            // orders the copy stream behind the composite (no timing)
+    // device-side PNG stream (png.cu): code tables, per-segment staging, one stream buffer per frame slot
+    void* d_png_tables; unsigned int* d_png_staging; unsigned int* d_png_seg; unsigned long long* d_png_off;
+    uint8_t* d_png_stream[BHR_FRAME_SLOTS]; int png_n_seg; size_t png_capacity;
     int ev_valid;
     float tint[3];
 };
@@ -193,3 +196,4 @@ int bhr_launch_bloom_h_tma(bhr_ctx* ctx, int row0, int row1);
 int bhr_launch_bloom_v_fused(bhr_ctx* ctx, uint32_t flags, int row0, int row1, const void* F_host, const void* F_dev,
                              const float* const* row_src, float* dst_f32, uint8_t* dst_u8);
 int bhr_launch_blur_only(bhr_ctx* ctx);
+int bhr_launch_png_encode(bhr_ctx* ctx, int slot);

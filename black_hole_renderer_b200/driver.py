@@ -18,6 +18,7 @@ import numpy as np
 from PIL import Image
 
 from .lifecycle import advance_lifecycle_frame, init_lifecycle_system
+from .png_codec import png_container
 from .renderer import R_DISK_INNER_DEFAULT, R_DISK_OUTER_DEFAULT, Renderer, compute_edge_alpha
 from .skybox import load_or_generate_skybox
 
@@ -166,8 +167,21 @@ def video_ring(renderer, ring):
     return cache[:ring]
 
 
+def png_ring(renderer, ring):
+    """Ring of page-locked byte buffers for device-encoded PNG streams ({u32 bytes, u32 adler} + stream).  Sized for a
+    stream as long as the raw frame (rendered frames compress several times; a longer stream -- noise -- is fetched
+    into a temporary by Renderer.png_stream)."""
+    cache = getattr(renderer, "_png_ring", None)
+    if cache is None or len(cache) < ring:
+        size = 8 + min(renderer.png_stream_capacity(), 3 * renderer.width * renderer.height + 65536)
+        cache = list(cache or []) + [renderer.pinned_bytes(size) for _ in range(ring - len(cache or []))]
+        renderer._png_ring = cache
+    return cache[:ring]
+
+
 def run_video_frames(renderer, n_frames, fov, static_cam_pos, orbit, orbit_degrees, dt, rank=0, world_size=1,
-                     completed=(), sink=None, on_rendered=None, ring=None, depth=28, factories=None, timing=None):
+                     completed=(), sink=None, on_rendered=None, ring=None, depth=28, factories=None, timing=None,
+                     png=False):
     """The frame loop of render_video (render.py:4437-4458) for the frames `rank` owns.
 
     Pipelined: frames are enqueued without waiting (texture kernels, render, D2H into one of `ring`
@@ -184,6 +198,10 @@ def run_video_frames(renderer, n_frames, fov, static_cam_pos, orbit, orbit_degre
     which frame 60 b fixes for block b.  A block that still has frames to render therefore starts
     with the full texture pass + statistics of its first frame even when that frame is already done
     (resume), so resumed frames equal those of an uninterrupted run.
+    `png=True`: the frames leave the device as the deflate stream of their PNG file (csrc/png.cu) instead of raw
+    pixels; `sink(frame, stream)` then receives the zlib stream (uint8 view of the ring buffer).  Only as many bytes
+    as recent frames needed (+25 % + 64 KB) are copied per frame; a longer stream is completed by a second copy when
+    the frame is retired.
     `timing`: a dict that receives the host-side seconds spent in foreign ticks, in the texture pass + render
     calls of own frames, and blocked on the device (frame retirement, buffer reuse).
     Returns the number of frames rendered."""
@@ -196,18 +214,26 @@ def run_video_frames(renderer, n_frames, fov, static_cam_pos, orbit, orbit_degre
         frame_bytes = 3 * getattr(renderer, "width", 1920) * getattr(renderer, "height", 1080)
         ring = int(min(48, max(8, 300e6 // frame_bytes)))
     depth = max(1, min(depth, FRAME_SLOTS - 1, ring - 4))
-    bufs = video_ring(renderer, ring)
+    bufs = png_ring(renderer, ring) if png else video_ring(renderer, ring)
+    copied = [0] * ring                        # png: bytes of the stream the enqueued copy covers
+    png_need = None                            # png: longest stream among the recently retired frames
+    png_bytes = 0
     busy = [None] * ring                       # future of the sink still reading the buffer
     in_flight = []                             # (frame, slot) enqueued, not yet waited for
 
     def retire(item):
-        nonlocal t_wait
+        nonlocal t_wait, png_need, png_bytes
         frame_done, slot = item
         t0 = clock()
         renderer.wait_frame(slot % FRAME_SLOTS)    # (depth + 1 <= FRAME_SLOTS frames in flight)
         t_wait += clock() - t0
+        data = bufs[slot]
+        if png:
+            data = renderer.png_stream(bufs[slot], slot % FRAME_SLOTS, copied[slot])
+            png_need = data.size if png_need is None else max(data.size, int(0.9 * png_need))
+            png_bytes += data.size
         if sink is not None:
-            busy[slot] = sink(frame_done, bufs[slot])
+            busy[slot] = sink(frame_done, data)
 
     def block_has_work(first):
         return any(f not in completed for f in range(first, min(first + STATS_PERIOD, n_frames)))
@@ -227,7 +253,12 @@ def run_video_frames(renderer, n_frames, fov, static_cam_pos, orbit, orbit_degre
                 busy[slot] = None
             t0 = clock()
             advance_lifecycle_frame(renderer, factories, t, dt, recompute_stats=block_start)
-            renderer.render_u8_async(cam_pos, fov, bufs[slot], slot % FRAME_SLOTS, frame=0)
+            if png:
+                guess = None if png_need is None else int(1.25 * png_need) + 65536
+                copied[slot] = renderer.render_png_async(cam_pos, fov, bufs[slot], slot % FRAME_SLOTS, frame=0,
+                                                         copy_bytes=guess)
+            else:
+                renderer.render_u8_async(cam_pos, fov, bufs[slot], slot % FRAME_SLOTS, frame=0)
             t_own += clock() - t0
             in_flight.append((frame, slot))
             if len(in_flight) > depth:
@@ -250,6 +281,8 @@ def run_video_frames(renderer, n_frames, fov, static_cam_pos, orbit, orbit_degre
             b.result()
     if timing is not None:
         timing.update(host_foreign_ticks_s=t_tick, host_own_frames_s=t_own, host_blocked_on_device_s=t_wait)
+        if png:
+            timing.update(png_stream_bytes=png_bytes)
     return rendered
 
 
@@ -312,8 +345,19 @@ def render_video(renderer, width, height, n_frames, fps, output_path, fov, stati
             f.write(encode_png(img_u8, png_level))
         os.replace(tmp, path)                  # a crash never leaves a truncated frame under the final name
 
-    def sink(frame, img_u8):
-        jobs[frame] = pool.submit(save_png, os.path.join(temp_dir, f"frame_{frame:04d}.png"), img_u8)
+    # the deflate stream comes from the device (csrc/png.cu) unless BHR_PNG_DEVICE=0: the host then only frames it
+    # (chunk lengths, CRC-32) and writes the file
+    device_png = os.environ.get("BHR_PNG_DEVICE", "1") != "0" and hasattr(renderer, "render_png_async")
+
+    def save_stream(path, stream):
+        tmp = path + ".part"
+        with open(tmp, "wb") as f:
+            f.write(png_container(width, height, stream))
+        os.replace(tmp, path)
+
+    def sink(frame, data):
+        jobs[frame] = pool.submit(save_stream if device_png else save_png,
+                                  os.path.join(temp_dir, f"frame_{frame:04d}.png"), data)
         return jobs[frame]
 
     def harvest():
@@ -338,7 +382,7 @@ def render_video(renderer, width, height, n_frames, fps, output_path, fov, stati
             print(f"  [rank {rank}] frame {frame}/{n_frames}, {rendered / (time.time() - t_start):.1f} frames/s")
 
     rendered = run_video_frames(renderer, n_frames, fov, static_cam_pos, orbit, orbit_degrees,
-                                disk_rotation_speed, rank, world_size, completed, sink, on_rendered)
+                                disk_rotation_speed, rank, world_size, completed, sink, on_rendered, png=device_png)
     pool.shutdown(wait=True)
     write_progress()
     completed |= mine_done

@@ -1,0 +1,279 @@
+"""PNG frame files without host-side deflate: the bit-stream format shared by the device encoder
+(csrc/png.cu) and its pure-Python twin below.
+
+The reference writes every video frame as a PNG through PIL (render.py:4462-4467: zlib on the host,
+tens of ms per 1080p frame and core).  Here the GPU emits the deflate stream itself, so that a
+frame file costs the host one CRC and one write:
+
+  * scanlines are Sub-filtered (PNG filter type 1: byte - byte of the pixel to the left);
+  * the filtered stream is cut into 256-byte segments, one GPU thread each; inside a segment runs
+    of a repeated byte become (length, distance 1) matches, everything else literals;
+  * ONE dynamic-Huffman deflate block holds the whole frame.  Its code is STATIC: built once from a
+    model of Sub residuals of rendered frames (peaked at 0, +-1, +-2, ...; long zero runs), so
+    there is no per-frame histogram / tree pass, and its header is a constant bit string;
+  * the segments' bit strings are concatenated at bit granularity (prefix sum of their lengths),
+    the Adler-32 of the filtered stream comes from per-segment partial sums.
+
+Everything below is deterministic and has a CPU implementation (`encode_frame_reference`), which
+the tests hold to `zlib.decompress` / PIL and the device encoder to byte for byte.
+"""
+import heapq
+import struct
+import zlib
+
+import numpy as np
+
+SEGMENT = 256            # bytes of the filtered stream per device thread
+MIN_RUN = 4              # shortest run coded as a match
+MAX_MATCH = 258
+
+# deflate length codes (RFC 1951, 3.2.5): symbol 257 + k for lengths >= base[k], with extra bits
+_LEN_BASE = [3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258]
+_LEN_EXTRA = [0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0]
+_CL_ORDER = [16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15]
+
+
+def _huffman_lengths(freqs, max_len):
+    """Code lengths of a Huffman code for `freqs` (zero frequency -> length 0), limited to max_len bits by
+    flattening the frequencies until the tree fits."""
+    freqs = np.asarray(freqs, dtype=np.float64)
+    used = np.nonzero(freqs > 0)[0]
+    if len(used) == 1:
+        out = np.zeros(len(freqs), dtype=np.int64)
+        out[used[0]] = 1
+        return out
+    f = freqs.copy()
+    while True:
+        heap = [(f[s], int(s), None, None) for s in used]
+        heapq.heapify(heap)
+        tie = len(freqs)
+        while len(heap) > 1:
+            a = heapq.heappop(heap)
+            b = heapq.heappop(heap)
+            heapq.heappush(heap, (a[0] + b[0], tie, a, b))
+            tie += 1
+        lengths = np.zeros(len(freqs), dtype=np.int64)
+        stack = [(heap[0], 0)]
+        while stack:
+            node, d = stack.pop()
+            if node[2] is None:
+                lengths[node[1]] = max(d, 1)
+            else:
+                stack.append((node[2], d + 1))
+                stack.append((node[3], d + 1))
+        if lengths.max() <= max_len:
+            return lengths
+        f[used] = np.maximum(f[used], f[used].max() / (1 << (max_len - 2)))      # flatten and retry
+        f[used] = f[used] ** 0.9
+
+
+def _canonical_codes(lengths):
+    """Canonical Huffman codes (RFC 1951, 3.2.2) -> codes with their bits REVERSED, ready for LSB-first packing."""
+    lengths = np.asarray(lengths, dtype=np.int64)
+    max_len = int(lengths.max())
+    bl_count = np.bincount(lengths, minlength=max_len + 1)
+    bl_count[0] = 0
+    next_code = np.zeros(max_len + 2, dtype=np.int64)
+    code = 0
+    for bits in range(1, max_len + 1):
+        code = (code + bl_count[bits - 1]) << 1
+        next_code[bits] = code
+    out = np.zeros(len(lengths), dtype=np.int64)
+    for s, n in enumerate(lengths):
+        if n:
+            c = int(next_code[n])
+            next_code[n] += 1
+            out[s] = int(format(c, f"0{n}b")[::-1], 2)
+    return out
+
+
+class _BitWriter:
+    def __init__(self):
+        self.acc, self.n, self.out = 0, 0, bytearray()
+
+    def put(self, value, nbits):
+        self.acc |= int(value) << self.n
+        self.n += int(nbits)
+        while self.n >= 8:
+            self.out.append(self.acc & 255)
+            self.acc >>= 8
+            self.n -= 8
+
+    def bits(self):
+        return 8 * len(self.out) + self.n
+
+    def bytes_padded(self):
+        return bytes(self.out) + (bytes([self.acc & 255]) if self.n else b"")
+
+
+class StaticCode:
+    """The static Huffman code of the frame block: literal / length alphabet (286 symbols), distance alphabet (only
+    distance 1 is used), the block header bit string, and the per-length (symbol code + extra bits) table."""
+
+    def __init__(self):
+        # model of Sub residuals of rendered frames: a two-sided geometric distribution around 0 on top of a flat
+        # floor (star fields, disk edges), long zero runs (sky-less shadow, saturated highlights) as matches
+        r = np.arange(256)
+        dist = np.minimum(r, 256 - r).astype(np.float64)
+        lit = 1e6 * (0.55 * np.exp(-dist / 1.2) + 0.35 * np.exp(-dist / 6.0) + 0.10 * np.exp(-dist / 40.0)) + 40.0
+        lit[0] *= 2.0
+        lit[1] += 3000.0                                          # the filter-type byte of every scanline
+        freq = np.zeros(286)
+        freq[:256] = lit
+        freq[256] = 1.0                                           # end of block: once per frame
+        run_w = 2.5e4 * np.array([1.0 / (1 + 0.25 * k) for k in range(29)])
+        run_w[28] = 4e4                                           # length 258: the body of every long run
+        freq[257:286] = run_w
+        self.lit_len = _huffman_lengths(freq, 15)
+        self.lit_code = _canonical_codes(self.lit_len)
+        # distance alphabet: only symbol 0 (distance 1); a lone symbol gets a 1-bit code (RFC 1951 allows the
+        # incomplete one-code tree)
+        self.dist_len = np.zeros(30, dtype=np.int64)
+        self.dist_len[0] = 1
+        self.dist_code = _canonical_codes(self.dist_len)
+        self.header_bits, self.header_nbits = self._block_header()
+        # per match length 3..258: total bits and value of (length symbol code, extra bits, distance code)
+        self.match_bits = np.zeros(MAX_MATCH + 1, dtype=np.uint32)
+        self.match_nbits = np.zeros(MAX_MATCH + 1, dtype=np.uint32)
+        for length in range(3, MAX_MATCH + 1):
+            k = max(i for i, b in enumerate(_LEN_BASE) if b <= length)
+            if length == 258:
+                k = 28
+            sym = 257 + k
+            v, n = int(self.lit_code[sym]), int(self.lit_len[sym])
+            v |= (length - _LEN_BASE[k]) << n
+            n += _LEN_EXTRA[k]
+            v |= int(self.dist_code[0]) << n
+            n += int(self.dist_len[0])
+            assert n <= 32
+            self.match_bits[length], self.match_nbits[length] = v, n
+        self.eob_bits, self.eob_nbits = int(self.lit_code[256]), int(self.lit_len[256])
+
+    def _block_header(self):
+        """BFINAL = 1, BTYPE = 10 and the code-length tables (RFC 1951, 3.2.7) as (int value, bit count)."""
+        seq = list(self.lit_len) + list(self.dist_len[:1])        # HLIT = 286, HDIST = 1
+        # run-length code the sequence with symbols 16 (repeat previous 3-6), 17 (zeros 3-10), 18 (zeros 11-138)
+        syms = []
+        i = 0
+        while i < len(seq):
+            v = seq[i]
+            j = i
+            while j < len(seq) and seq[j] == v:
+                j += 1
+            run = j - i
+            if v == 0 and run >= 3:
+                while run >= 11:
+                    n = min(run, 138); syms.append((18, n - 11, 7)); run -= n
+                if run >= 3:
+                    syms.append((17, run - 3, 3)); run = 0
+                syms += [(0, 0, 0)] * run
+            else:
+                syms.append((v, 0, 0)); run -= 1
+                while run >= 3:
+                    n = min(run, 6); syms.append((16, n - 3, 2)); run -= n
+                syms += [(v, 0, 0)] * run
+            i = j
+        cl_freq = np.bincount([s for s, _, _ in syms], minlength=19)
+        cl_len = _huffman_lengths(cl_freq, 7)
+        cl_code = _canonical_codes(cl_len)
+        hclen = 19
+        while hclen > 4 and cl_len[_CL_ORDER[hclen - 1]] == 0:
+            hclen -= 1
+        w = _BitWriter()
+        w.put(1, 1); w.put(2, 2)                                  # BFINAL, BTYPE = dynamic
+        w.put(286 - 257, 5); w.put(1 - 1, 5); w.put(hclen - 4, 4)
+        for k in range(hclen):
+            w.put(int(cl_len[_CL_ORDER[k]]), 3)
+        for s, extra, nextra in syms:
+            w.put(int(cl_code[s]), int(cl_len[s]))
+            if nextra:
+                w.put(extra, nextra)
+        nbits = w.bits()
+        return int.from_bytes(w.bytes_padded(), "little"), nbits
+
+    def device_tables(self):
+        """(lit_bits u32[256], lit_nbits u32[256], match_bits u32[259], match_nbits u32[259], header bytes, header bit
+        count, eob bits, eob bit count) -- what csrc/png.cu uploads."""
+        hdr = self.header_bits.to_bytes((self.header_nbits + 7) // 8, "little")
+        return (self.lit_code[:256].astype(np.uint32), self.lit_len[:256].astype(np.uint32), self.match_bits.copy(),
+                self.match_nbits.copy(), hdr, self.header_nbits, self.eob_bits, self.eob_nbits)
+
+
+_CODE = None
+
+
+def static_code():
+    global _CODE
+    if _CODE is None:
+        _CODE = StaticCode()
+    return _CODE
+
+
+def sub_filter(img_u8):
+    """(H, W, 3) u8 -> the filtered byte stream of the PNG (filter type 1 on every scanline), 1-D u8."""
+    h, w, c = img_u8.shape
+    rows = np.ascontiguousarray(img_u8).reshape(h, w * c)
+    raw = np.empty((h, w * c + 1), np.uint8)
+    raw[:, 0] = 1
+    raw[:, 1:] = rows
+    raw[:, 1 + c:] -= rows[:, :-c]
+    return raw.reshape(-1)
+
+
+def tokenize_segment(seg):
+    """[(kind, value)]: ('L', byte) literals and ('M', length) distance-1 matches of one segment (runs never look
+    back across the segment's first byte, so segments are independent)."""
+    out, i, n = [], 0, len(seg)
+    while i < n:
+        if i > 0 and seg[i] == seg[i - 1]:
+            k = 1
+            while i + k < n and k < MAX_MATCH and seg[i + k] == seg[i - 1]:
+                k += 1
+            if k >= MIN_RUN:
+                out.append(("M", k))
+                i += k
+                continue
+        out.append(("L", int(seg[i])))
+        i += 1
+    return out
+
+
+def encode_stream_reference(filtered):
+    """zlib stream (header, one dynamic block, Adler-32) of a filtered byte stream; also returns per-segment bit
+    counts (what the device's prefix sum works on)."""
+    code = static_code()
+    w = _BitWriter()
+    w.put(0x78, 8); w.put(0x01, 8)
+    w.put(code.header_bits, code.header_nbits)
+    seg_bits = []
+    for s in range(0, len(filtered), SEGMENT):
+        before = w.bits()
+        for kind, v in tokenize_segment(filtered[s:s + SEGMENT]):
+            if kind == "L":
+                w.put(int(code.lit_code[v]), int(code.lit_len[v]))
+            else:
+                w.put(int(code.match_bits[v]), int(code.match_nbits[v]))
+        seg_bits.append(w.bits() - before)
+    w.put(code.eob_bits, code.eob_nbits)
+    return w.bytes_padded() + struct.pack(">I", zlib.adler32(filtered.tobytes())), seg_bits
+
+
+def png_container(width, height, zlib_stream):
+    """PNG file bytes around a finished zlib stream (8-bit RGB, no interlace)."""
+    def chunk(tag, payload):
+        return struct.pack(">I", len(payload)) + tag + payload + struct.pack(">I", zlib.crc32(payload, zlib.crc32(tag)))
+    return (b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", width, height, 8, 2, 0, 0, 0))
+            + chunk(b"IDAT", bytes(zlib_stream)) + chunk(b"IEND", b""))
+
+
+def encode_frame_reference(img_u8):
+    """CPU twin of the device encoder: (H, W, 3) u8 -> PNG file bytes."""
+    h, w, _ = img_u8.shape
+    stream, _ = encode_stream_reference(sub_filter(img_u8))
+    return png_container(w, h, stream)
+
+
+def stream_capacity(width, height):
+    """Upper bound of the zlib stream's size in bytes: every byte a 15-bit literal + header, EOB, Adler-32."""
+    n = height * (3 * width + 1)
+    return 2 + (static_code().header_nbits + 15 * n + 15 + 7) // 8 + 4 + 64

@@ -281,6 +281,75 @@ class Renderer:
     def wait_frame(self, slot):
         self._check(self._lib.bhr_wait_frame(self._ctx, int(slot)))
 
+    # ---- frame files: the PNG's deflate stream from the device (csrc/png.cu, png_codec.py) ----
+    def _png_setup(self):
+        if getattr(self, "_png_capacity", None) is None:
+            from . import png_codec
+            t = png_codec.static_code().device_tables()
+            u32 = lambda a: a.ctypes.data_as(C.POINTER(C.c_uint32))
+            keep = [np.ascontiguousarray(a, np.uint32) for a in t[:4]]
+            header = np.frombuffer(t[4], np.uint8).copy()
+            self._check(self._lib.bhr_png_setup(self._ctx, *(u32(a) for a in keep),
+                                                header.ctypes.data_as(C.POINTER(C.c_uint8)), int(t[5]),
+                                                int(t[6]), int(t[7])))
+            cap = C.c_size_t()
+            self._check(self._lib.bhr_png_capacity(self._ctx, C.byref(cap)))
+            self._png_capacity = int(cap.value)
+        return self._png_capacity
+
+    def png_stream_capacity(self):
+        """Upper bound (bytes) of one frame's zlib stream; `pinned_bytes(8 + capacity)` holds any frame."""
+        return self._png_setup()
+
+    def pinned_bytes(self, n):
+        """A pinned uint8 array of n bytes (freed with the renderer)."""
+        p = C.c_void_p()
+        if self._lib.bhr_host_alloc(int(n), C.byref(p)) != 0:
+            raise L.BhrError("bhr_host_alloc failed")
+        self.__dict__.setdefault("_pinned", []).append(p)
+        return np.frombuffer((C.c_char * int(n)).from_address(p.value), dtype=np.uint8)
+
+    def render_png_async(self, cam_pos, fov, buf, slot, frame=0, copy_bytes=None, skip_differentials=False,
+                         skip_bloom=False):
+        """Like render_u8_async, but what reaches the host is the frame's PNG deflate stream: `buf` (pinned uint8,
+        from pinned_bytes) receives {u32 stream_bytes, u32 adler32} + the first copy_bytes of the stream
+        (default: all that fits buf).  After wait_frame(slot), `png_file_bytes(buf, slot)` is the file."""
+        self._png_setup()
+        cam = self._camera(cam_pos, fov, frame)
+        assert buf.dtype == np.uint8 and buf.flags.c_contiguous and buf.ndim == 1 and buf.size > 8
+        room = buf.size - 8
+        copy_bytes = room if copy_bytes is None else max(0, min(int(copy_bytes), room))
+        self._check(self._lib.bhr_render_async_png(self._ctx, C.byref(cam), self._flags(skip_differentials, skip_bloom),
+                                                   buf.ctypes.data, copy_bytes, int(slot)))
+        self._disk_post_bloom = not skip_bloom
+        return copy_bytes
+
+    def png_stream(self, buf, slot, copied):
+        """The complete zlib stream of slot's frame as a uint8 view/array (after wait_frame): the bytes already in
+        `buf`, plus a synchronous fetch of the remainder when the stream was longer than `copied`."""
+        n = int(buf[:4].view(np.uint32)[0])
+        if n <= copied:
+            return buf[8:8 + n]
+        out = buf[8:]
+        if n > out.size:                        # longer than the ring buffer (incompressible frame): a temporary
+            out = np.empty(n, np.uint8)
+            out[:copied] = buf[8:8 + copied]
+        self._check(self._lib.bhr_png_fetch(self._ctx, int(slot), copied, n - copied, out.ctypes.data + copied))
+        return out[:n]
+
+    def png_file_bytes(self, buf, slot, copied):
+        from . import png_codec
+        return png_codec.png_container(self.width, self.height, self.png_stream(buf, slot, copied))
+
+    def encode_png_current(self):
+        """PNG file bytes of the frame currently on the device (after render / render_u8 / render_device)."""
+        from . import png_codec
+        cap = self._png_setup()
+        out = np.empty(cap, np.uint8)
+        n = C.c_uint32()
+        self._check(self._lib.bhr_png_encode_current(self._ctx, out.ctypes.data, cap, C.byref(n)))
+        return png_codec.png_container(self.width, self.height, out[:n.value])
+
     def render_device(self, cam_pos, fov, frame=0, skip_differentials=False, skip_bloom=False,
                       aux=False):
         """Enqueue one frame and leave the results in device buffers (no host copy, no sync)."""

@@ -147,6 +147,26 @@ int bhr_render(bhr_ctx* ctx, const bhr_camera* cam, uint32_t flags, float* out_f
 int bhr_render_async(bhr_ctx* ctx, const bhr_camera* cam, uint32_t flags, float* out_f32, uint8_t* out_u8, int slot);
 int bhr_wait_frame(bhr_ctx* ctx, int slot);
 
+/* ---- frame files: the PNG's deflate stream produced on the device ----
+ * Replaces the host-side PIL save of every video frame (render.py:4462-4467, render_video) by three small
+ * kernels after the composite: Sub-filtered scanlines, byte runs as (length, distance 1) matches, a static
+ * Huffman code (format + CPU twin: black_hole_renderer_b200/png_codec.py).  What reaches the host is the
+ * complete zlib stream of the IDAT chunk; the host adds the chunk framing and CRC-32 and writes the file.
+ * bhr_png_setup uploads the code tables once per context (png_codec.StaticCode.device_tables()). */
+int bhr_png_setup(bhr_ctx* ctx, const uint32_t* lit_bits, const uint32_t* lit_nbits, const uint32_t* match_bits,
+                  const uint32_t* match_nbits, const uint8_t* header, uint32_t header_nbits, uint32_t eob_bits,
+                  uint32_t eob_nbits);
+/* upper bound of a frame's stream length in bytes (size of the host buffers below, without the 8-byte prefix) */
+int bhr_png_capacity(bhr_ctx* ctx, size_t* stream_bytes);
+/* bhr_render_async whose result is the stream: `host` (pinned, >= 8 + copy_bytes) receives
+ * {uint32 stream_bytes, uint32 adler32} and the first copy_bytes of the stream.  A caller may pass a
+ * copy_bytes smaller than the capacity (e.g. the previous frame's length + margin); when stream_bytes turns
+ * out larger it reads the remainder with bhr_png_fetch before the slot is reused. */
+int bhr_render_async_png(bhr_ctx* ctx, const bhr_camera* cam, uint32_t flags, void* host, size_t copy_bytes, int slot);
+int bhr_png_fetch(bhr_ctx* ctx, int slot, size_t offset, size_t bytes, void* host);
+/* stream of the frame currently in BHR_BUF_FINAL_U8, synchronously */
+int bhr_png_encode_current(bhr_ctx* ctx, void* host, size_t host_bytes, uint32_t* stream_bytes);
+
 /* Row-tile variants used when one frame is split over several GPUs.  Stage 1 ray
  * marches rows [row0, row1) and runs the horizontal bloom pass on them; the caller then exchanges
  * the radius-row halos of BHR_BUF_HBLUR between neighbours (NCCL) and, for the flare, all-reduces

@@ -159,3 +159,59 @@ def test_encode_png_round_trips_through_pil(tmp_path):
     sliced = rng.integers(0, 256, size=(20, 30, 3), dtype=np.uint8)[::2, ::3]      # non-contiguous input
     (tmp_path / "s.png").write_bytes(encode_png(sliced))
     assert np.array_equal(np.array(Image.open(tmp_path / "s.png")), sliced)
+
+
+class FakePngRenderer(FakeRenderer):
+    """Stands in for the device PNG path: render_png_async fills the ring buffer with {bytes, adler} + the stream of
+    the CPU twin encoder, honouring copy_bytes; png_stream completes short copies the way Renderer.png_stream does."""
+    width, height = 8, 4
+
+    def png_stream_capacity(self):
+        from black_hole_renderer_b200 import png_codec
+        return png_codec.stream_capacity(self.width, self.height)
+
+    def pinned_bytes(self, n):
+        return np.zeros(n, np.uint8)
+
+    def render_png_async(self, cam_pos, fov, buf, slot, frame=0, copy_bytes=None):
+        from black_hole_renderer_b200 import png_codec
+        self.cams.append(list(cam_pos))
+        self.slots = getattr(self, "slots", []) + [slot]
+        img = np.full((self.height, self.width, 3), len(self.cams) % 251, np.uint8)
+        img[0, 0, 0] = (7 * len(self.cams)) % 256
+        stream, _ = png_codec.encode_stream_reference(png_codec.sub_filter(img))
+        stream = np.frombuffer(bytes(stream), np.uint8)
+        self.full = getattr(self, "full", {})
+        self.full[slot] = stream
+        room = buf.size - 8
+        copy_bytes = room if copy_bytes is None else min(copy_bytes, room)
+        if getattr(self, "starve", False):
+            copy_bytes = min(copy_bytes, 5)     # force the second-copy path
+        buf[:4] = np.array([stream.size], np.uint32).view(np.uint8)
+        n = min(copy_bytes, stream.size)
+        buf[8:8 + n] = stream[:n]
+        self.copies = getattr(self, "copies", []) + [copy_bytes]
+        return copy_bytes
+
+    def png_stream(self, buf, slot, copied):
+        n = int(buf[:4].view(np.uint32)[0])
+        if n > copied:
+            self.fetches = getattr(self, "fetches", 0) + 1
+            buf[8 + copied:8 + n] = self.full[slot][copied:n]
+        return buf[8:8 + n]
+
+
+def test_device_png_streams_become_the_frame_files(tmp_path):
+    from PIL import Image
+    for starve in (False, True):
+        r = FakePngRenderer()
+        r.starve = starve
+        sub = tmp_path / f"s{int(starve)}"
+        sub.mkdir()
+        d = _run(sub, r, n_frames=40, degrees=90.0)
+        for f in range(40):
+            img = np.array(Image.open(d / f"frame_{f:04d}.png"))
+            assert img.shape == (4, 8, 3) and img[0, 0, 0] == (7 * (f + 1)) % 256 and np.all(img[1:] == (f + 1) % 251)
+        assert (getattr(r, "fetches", 0) > 0) == starve
+        # after the first frames retire, the copy size follows the streams instead of the buffer size
+        assert starve or r.copies[-1] <= r.copies[0]
