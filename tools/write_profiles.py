@@ -50,12 +50,13 @@ def launches(csv_in, md_out, bench_log):
         v = v / 1000 if r[iu] == 'ns' else v * 1000 if r[iu] == 'ms' else v
         agg.setdefault(r[ik].split('(')[0].replace('void ', '').replace('<unnamed>::', ''), []).append(v)
     bench = json.loads(open(os.path.join(G, bench_log)).read().strip().splitlines()[-1])
-    frame = ['band_list_kernel', 'raymarch_persistent<0, 768, 0>', 'retrace_kernel<0>', 'bloom_h_kernel', 'bloom_v_kernel<0>', 'composite_kernel<1, 4, 0>']
+    frame = ['band_list_kernel', 'raymarch_persistent<0, 768, 0>', 'retrace_kernel<0>']
+    frame += [k for k in agg if k.startswith(('bloom_h', 'bloom_v', 'composite_kernel', 'flare_add'))]
     med = lambda v: sorted(v)[len(v) // 2]      # (median: the banded synchronous frames of the e2e block launch the same kernels on row bands)
     tot = sum(med(agg[k]) for k in frame if k in agg)
     with open(os.path.join(P, md_out), "w") as f:
         f.write(f"# {TAG} launch list summary (profiles/{csv_in})\n\n")
-        f.write("Command: `ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-other-configs`\n"
+        f.write("Command: `ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-other-configs --no-orbit --no-tiled`\n"
                 f"(after the same command exited 0 without ncu: ms_per_step {bench['ms_per_step']:.4f}, stage_ms {bench['stage_ms']}).\n"
                 "Per-launch times under ncu are cold-cache and serialised: compare SHARES with bench.py's stage_ms, not absolutes.\n\n")
         f.write("| kernel | launches | median us | share of one frame |\n|---|---|---|---|\n")
@@ -78,4 +79,5 @@ if __name__ == "__main__":
     summarise(f"{TAG}_raymarch.ncu-rep", f"{TAG}_raymarch_ncu.txt", "ncu --set full --clock-control none: fhd default scene (tools/prof_fhd.py fhd 0 3), ray-march kernels")
     summarise(f"{TAG}_post.ncu-rep", f"{TAG}_post_ncu.txt", "ncu --set full --clock-control none: fhd default scene, bloom H / bloom V / composite")
     summarise(f"{TAG}_raymarch_4k_aa.ncu-rep", f"{TAG}_raymarch_4k_aa_ncu.txt", "ncu --set full --clock-control none: 4K, anti_alias lod_radius, tilt 20, flare (BASELINE configs[2]) ray march with differentials")
+    summarise(f"{TAG}_png.ncu-rep", f"{TAG}_png_ncu.txt", "ncu --set full --clock-control none: device PNG encoder (tools/prof_png.py), fhd default scene frame")
     summarise(f"{TAG}_texture.ncu-rep", f"{TAG}_texture_ncu.txt", "ncu --set full --clock-control none: disk-texture pipeline kernels of a video frame (tools/video_breakdown.py)")
