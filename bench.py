@@ -231,6 +231,22 @@ def d2h_probe(r, torch, dist, rank, world, nbytes, reps=8):
             "concurrent_gbs_total": round(sum(v[world:]), 2)}
 
 
+def nvlink_kib(index):
+    """(tx, rx) KiB moved over all NVLink links of GPU `index` since driver load (NVML throughput counters, payload
+    bytes), or None when NVML does not expose them."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        v = pynvml.nvmlDeviceGetFieldValues(h, [(pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX, 0xffffffff),
+                                                (pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX, 0xffffffff)])
+        if any(x.nvmlReturn != 0 for x in v):
+            return None
+        return int(v[0].value.ullVal), int(v[1].value.ullVal)
+    except Exception:
+        return None
+
+
 def tiled_4k(Renderer, sky, rank, world, local, dist, torch, frames=8):
     """BASELINE.json configs[2]: one 4K frame (anti_alias lod_radius, tilt 20, lens flare, lifecycle
     texture 832 x 5824) row-tiled over the ranks; 8-bit frame in rank 0's host memory at the end of
@@ -308,7 +324,34 @@ def tiled_4k(Renderer, sky, rank, world, local, dist, torch, frames=8):
     compare("nccl", frame)
     D.attach_peers(r, rank, world)
     frame, dev_ms, host_ms = timed(lambda: D.render_tiled_peer(r, POV, FOV))
+    # NVLink evidence for the peer path: rate at which every rank reads its right-hand neighbour's H-blurred layer
+    # (99.5 MB at 4K) through the CUDA-IPC mapping with the halo pull's access pattern, one rank at a time and all
+    # together; PCIe 5 x16 cannot carry more than 64 GB/s
+    import ctypes as C
+    def probe():
+        g = C.c_double()
+        r._check(r._lib.bhr_peer_probe_read(r._ctx, (rank + 1) % world, 4, C.byref(g)))
+        return g.value
+    alone = 0.0
+    for k in range(world):
+        dist.barrier()
+        if k == rank:
+            alone = probe()
+    dist.barrier()
+    together = probe()
+    pr = torch.tensor([alone, together], dtype=torch.float64, device="cuda")
+    gathered = [torch.zeros_like(pr) for _ in range(world)]
+    dist.all_gather(gathered, pr)
+    R = r._lib.bhr_bloom_radius(r._ctx)
+    rows = H // world
+    nv = {"peer_read_gbs_alone_per_rank": [round(float(g[0]), 1) for g in gathered],
+          "peer_read_gbs_all_ranks_at_once": [round(float(g[1]), 1) for g in gathered],
+          "halo_bytes_pulled_per_frame_inner_rank": 2 * min(R, rows) * W * 3 * 4,
+          "tile_bytes_stored_to_rank0_per_frame": rows * W * 3,
+          "nvml_link_counters": "not exposed in this VM (nvmlDeviceGetFieldValues NVLINK_THROUGHPUT returns not supported)"
+                                if nvlink_kib(local) is None else "available"}
     out["peer"] = {"ms": dev_ms, "host_clock_ms": host_ms,
+                   "nvlink_evidence": nv,
                    "path": "csrc/peer.cu: V pass loads halo rows from the neighbours' HBM, composite stores into rank 0's "
                            "buffers, release/acquire flags; equal-height tiles; rank 0 copies the frame out"}
     compare("peer", frame)

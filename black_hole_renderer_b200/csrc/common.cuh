@@ -129,6 +129,8 @@ struct bhr_ctx {
     // device-side PNG stream (png.cu): code tables, per-segment staging, one stream buffer per frame slot
     void* d_png_tables; unsigned int* d_png_staging; unsigned int* d_png_seg; unsigned long long* d_png_off;
     uint8_t* d_png_stream[BHR_FRAME_SLOTS]; int png_n_seg; size_t png_capacity;
+    // the entity layer runs on its own stream next to the background kernel (texture.cu): FP64-bound beside FP32-bound
+    cudaStream_t ent_stream; cudaEvent_t bg_start_ev, ent_done_ev; int bg_start_armed, ent_pending, entity_stream_on;
     int ev_valid;
     float tint[3];
 };
@@ -150,6 +152,15 @@ extern char g_bhr_create_error[512];
         snprintf((ctx)->err, sizeof((ctx)->err), __VA_ARGS__);     \
         return (code);                                             \
     } while (0)
+
+// Work on the context's stream that reads or writes the entity planes of `comp` first waits for the entity stream.
+static inline int bhr_join_entities(bhr_ctx* ctx) {
+    if (ctx->ent_pending) {
+        BHR_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ent_done_ev, 0));
+        ctx->ent_pending = 0;
+    }
+    return BHR_OK;
+}
 
 // Every entry point that touches the device runs with the context's GPU current and restores the
 // caller's device afterwards: a process may hold contexts on several GPUs, and hosts such as torch

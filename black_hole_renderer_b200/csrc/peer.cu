@@ -305,6 +305,36 @@ static int render_tiled_peer_body(bhr_ctx* ctx, const bhr_camera* cam, uint32_t 
     return BHR_OK;
 }
 
+// Measurement hook: the H-blurred layer of `peer` (3 x H x W floats in that GPU's HBM, mapped with CUDA IPC) is read
+// `reps` times by a plain 16-byte-load kernel -- the access pattern of the halo pull -- into this rank's blur
+// scratch layer; GB/s by CUDA events.  A rate above what PCIe can carry (64 GB/s) shows the mapping goes over NVLink.
+__global__ void __launch_bounds__(256) peer_probe_kernel(float4* __restrict__ dst, const float4* __restrict__ src, size_t n4) {
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (size_t)gridDim.x * 256) dst[i] = src[i];
+}
+
+extern "C" int bhr_peer_probe_read(bhr_ctx* ctx, int peer, int reps, double* gbs) {
+    BhrDeviceGuard device_guard_(ctx);
+    if (!ctx || !gbs || reps < 1) return BHR_ERR_INVALID;
+    if (peer < 0 || peer >= ctx->peer_world || !ctx->peer_hblur[peer]) BHR_FAIL(ctx, BHR_ERR_STATE, "rank %d is not attached", peer);
+    const size_t n4 = (size_t)ctx->W * ctx->H * 3 / 4;
+    cudaEvent_t e0, e1;
+    BHR_CUDA(ctx, cudaEventCreate(&e0));
+    BHR_CUDA(ctx, cudaEventCreate(&e1));
+    const int grid = ctx->num_sms * 8;
+    peer_probe_kernel<<<grid, 256, 0, ctx->stream>>>((float4*)ctx->blur, (const float4*)ctx->peer_hblur[peer], n4);
+    BHR_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+    for (int k = 0; k < reps; ++k) peer_probe_kernel<<<grid, 256, 0, ctx->stream>>>((float4*)ctx->blur, (const float4*)ctx->peer_hblur[peer], n4);
+    BHR_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+    BHR_CUDA(ctx, cudaEventSynchronize(e1));
+    float ms = 0.0f;
+    BHR_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    ctx->launches += reps + 1;
+    *gbs = (double)n4 * 16.0 * reps / (ms * 1e-3) / 1e9;
+    return BHR_OK;
+}
+
 extern "C" int bhr_peer_set_distributed_egress(bhr_ctx* ctx, int enabled) {
     if (!ctx) return BHR_ERR_INVALID;
     ctx->peer_distributed = enabled ? 1 : 0;

@@ -195,6 +195,7 @@ extern "C" int bhr_stats_prepare(bhr_ctx* ctx, int enable_rt, uint64_t* n_total,
     if (!ctx->bg_ready) BHR_FAIL(ctx, BHR_ERR_STATE, "Must call init_background_layer() first");
     int rc = ensure_stats_storage(ctx);
     if (rc) return rc;
+    if ((rc = bhr_join_entities(ctx))) return rc;
     const size_t plane = (size_t)ctx->n_r * ctx->n_phi;
     float* dens = ctx->stats_scratch;
     float* strc = dens + plane;

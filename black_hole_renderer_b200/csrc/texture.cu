@@ -416,6 +416,13 @@ extern "C" int bhr_generate_background(bhr_ctx* ctx, float t) {
     BhrDeviceGuard device_guard_(ctx);
     if (!ctx) return BHR_ERR_INVALID;
     if (!ctx->bg_ready) BHR_FAIL(ctx, BHR_ERR_STATE, "Must call init_background_layer() first");
+    if (ctx->entity_stream_on) {
+        // the entity layer of the same frame (bhr_accumulate_entities, its own stream) may start with this kernel: the two
+        // write different planes of `comp`, and everything that read the old planes is ahead of this point on the stream
+        if (!ctx->bg_start_ev) BHR_CUDA(ctx, cudaEventCreateWithFlags(&ctx->bg_start_ev, cudaEventDisableTiming));
+        BHR_CUDA(ctx, cudaEventRecord(ctx->bg_start_ev, ctx->stream));
+        ctx->bg_start_armed = 1;
+    }
     if (!ctx->background_scalar) return bhr_launch_background(ctx, t);       // background.cu: two texels per thread, packed
     // one texel per thread, row quantities per block (option "background_scalar": A/B reference of the packed kernel);
     // one block per (row, column chunk), the block width that wastes the fewest lanes on the ragged last chunk
@@ -438,8 +445,24 @@ extern "C" int bhr_accumulate_entities(bhr_ctx* ctx, const bhr_entity* entities,
     // host staging ring (pinned): the caller's array may be reused as soon as we return, and the
     // upload must not wait for the frames still in flight on the stream
     const int n_slots_ring = BHR_FRAME_SLOTS;
+    // Stream: the entity kernels are FP64-bound, the background kernel FP32-bound; on their own stream, released by the
+    // event bhr_generate_background records in front of its kernel (or, without one, by everything enqueued so far),
+    // they share the SMs with it.  Readers of the entity planes join through bhr_join_entities.
+    cudaStream_t es = ctx->stream;
+    if (ctx->entity_stream_on) {
+        if (!ctx->ent_stream) {
+            BHR_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->ent_stream, cudaStreamNonBlocking));
+            BHR_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ent_done_ev, cudaEventDisableTiming));
+        }
+        if (!ctx->bg_start_ev) BHR_CUDA(ctx, cudaEventCreateWithFlags(&ctx->bg_start_ev, cudaEventDisableTiming));
+        if (!ctx->bg_start_armed) BHR_CUDA(ctx, cudaEventRecord(ctx->bg_start_ev, ctx->stream));
+        ctx->bg_start_armed = 0;
+        es = ctx->ent_stream;
+        BHR_CUDA(ctx, cudaStreamWaitEvent(es, ctx->bg_start_ev, 0));
+    }
     if (n > ctx->entities_cap) {
         BHR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->ent_stream) BHR_CUDA(ctx, cudaStreamSynchronize(ctx->ent_stream));
         if (ctx->d_entities) cudaFree(ctx->d_entities);
         if (ctx->h_entities) cudaFreeHost(ctx->h_entities);
         if (ctx->d_coltab) cudaFree(ctx->d_coltab);
@@ -464,7 +487,8 @@ extern "C" int bhr_accumulate_entities(bhr_ctx* ctx, const bhr_entity* entities,
     }
     const size_t plane = (size_t)ctx->n_r * ctx->n_phi;
     if (n == 0) {
-        BHR_CUDA(ctx, cudaMemsetAsync(ctx->comp + 5 * plane, 0, 6 * plane * sizeof(float), ctx->stream));
+        BHR_CUDA(ctx, cudaMemsetAsync(ctx->comp + 5 * plane, 0, 6 * plane * sizeof(float), es));
+        if (es != ctx->stream) { BHR_CUDA(ctx, cudaEventRecord(ctx->ent_done_ev, es)); ctx->ent_pending = 1; }
         return BHR_OK;
     }
     const int ring = ctx->ent_ring;
@@ -481,14 +505,14 @@ extern "C" int bhr_accumulate_entities(bhr_ctx* ctx, const bhr_entity* entities,
     for (int e = 0; e < n; ++e) {
         if (entities[e].kind == 1 || entities[e].kind == 2) { h_slot[e] = n_tab; h_slot_ent[n_tab++] = e; } else h_slot[e] = -1;
     }
-    BHR_CUDA(ctx, cudaMemcpyAsync(d, h, per, cudaMemcpyHostToDevice, ctx->stream));
+    BHR_CUDA(ctx, cudaMemcpyAsync(d, h, per, cudaMemcpyHostToDevice, es));
     const bhr_entity* d_ent = (const bhr_entity*)d;
     const int* d_slot = (const int*)(d + (size_t)ctx->entities_cap * sizeof(bhr_entity));
     const int* d_slot_ent = d_slot + ctx->entities_cap;
     double* coltab = ctx->d_coltab + (size_t)(ring & 1) * ctx->entities_cap * ctx->n_phi;
     if (n_tab > 0) {
         dim3 g(bhr_div_up(ctx->n_phi, 256), n_tab);
-        entity_coltab_kernel<<<g, 256, 0, ctx->stream>>>(d_ent, d_slot_ent, ctx->n_phi, coltab);
+        entity_coltab_kernel<<<g, 256, 0, es>>>(d_ent, d_slot_ent, ctx->n_phi, coltab);
         ++ctx->launches;
     }
     const size_t smem = (size_t)n * sizeof(RowEntity);
@@ -496,11 +520,12 @@ extern "C" int bhr_accumulate_entities(bhr_ctx* ctx, const bhr_entity* entities,
     if (smem > 48 * 1024)
         BHR_CUDA(ctx, cudaFuncSetAttribute(entity_accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(bhr_div_up(ctx->n_phi, kEntCols), ctx->n_r);
-    entity_accumulate_kernel<<<grid, 256, smem, ctx->stream>>>(ctx->comp, ctx->n_r, ctx->n_phi, d_ent, n, ctx->omega_rows,
+    entity_accumulate_kernel<<<grid, 256, smem, es>>>(ctx->comp, ctx->n_r, ctx->n_phi, d_ent, n, ctx->omega_rows,
                                                                d_slot, coltab, ctx->d_entity_tables);
     ++ctx->launches;
     BHR_CUDA(ctx, cudaGetLastError());
-    BHR_CUDA(ctx, cudaEventRecord(ctx->ent_ev[ring], ctx->stream));
+    BHR_CUDA(ctx, cudaEventRecord(ctx->ent_ev[ring], es));
+    if (es != ctx->stream) { BHR_CUDA(ctx, cudaEventRecord(ctx->ent_done_ev, es)); ctx->ent_pending = 1; }
     return BHR_OK;
 }
 
@@ -510,6 +535,7 @@ extern "C" int bhr_upload_entity_tables(bhr_ctx* ctx, const float* data, size_t 
     BhrDeviceGuard device_guard_(ctx);
     if (!ctx || (n_floats > 0 && !data)) return BHR_ERR_INVALID;
     BHR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));           // kernels of earlier frames may still read the old buffer
+    if (ctx->ent_stream) BHR_CUDA(ctx, cudaStreamSynchronize(ctx->ent_stream));
     if (n_floats > ctx->entity_tables_cap) {
         if (ctx->d_entity_tables) cudaFree(ctx->d_entity_tables);
         ctx->d_entity_tables = nullptr;
@@ -537,6 +563,7 @@ extern "C" int bhr_upload_comp(bhr_ctx* ctx, const float* comp) {
     if (!ctx || !comp) return BHR_ERR_INVALID;
     if (!ctx->bg_ready) BHR_FAIL(ctx, BHR_ERR_STATE, "Must call init_background_layer() first");
     const size_t bytes = (size_t)ctx->n_r * ctx->n_phi * BHR_N_COMP * sizeof(float);
+    if (int rc = bhr_join_entities(ctx)) return rc;
     BHR_CUDA(ctx, cudaMemcpyAsync(ctx->comp, comp, bytes, cudaMemcpyHostToDevice, ctx->stream));
     BHR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return BHR_OK;
@@ -547,6 +574,7 @@ extern "C" int bhr_compose_texture(bhr_ctx* ctx, float t_offset, int enable_rt, 
     if (!ctx) return BHR_ERR_INVALID;
     if (!ctx->bg_ready) BHR_FAIL(ctx, BHR_ERR_STATE, "Must call init_background_layer() first");
     const size_t plane = (size_t)ctx->n_r * ctx->n_phi;
+    if (int rc = bhr_join_entities(ctx)) return rc;
     compose_kernel<<<(unsigned)((plane + 255) / 256), 256, 0, ctx->stream>>>(
         ctx->comp, ctx->omega_rows, ctx->edge, ctx->stats[0], ctx->stats[1], ctx->row_stats, ctx->n_r, ctx->n_phi,
         t_offset, enable_rt, color_temp, ctx->mips);

@@ -200,6 +200,9 @@ int bhr_peer_export(bhr_ctx* ctx, bhr_ipc_handle out[4]);
 int bhr_peer_attach(bhr_ctx* ctx, int rank, int world, const bhr_ipc_handle* all);
 int bhr_render_tiled_peer(bhr_ctx* ctx, const bhr_camera* cam, uint32_t flags, float* out_f32, uint8_t* out_u8);
 int bhr_peer_set_distributed_egress(bhr_ctx* ctx, int enabled);   /* all ranks, before the first frame */
+/* measurement hook: GB/s at which this rank reads rank `peer`'s H-blurred layer through the peer mapping (the halo
+ * pull's access pattern); above PCIe's 64 GB/s the mapping is NVLink */
+int bhr_peer_probe_read(bhr_ctx* ctx, int peer, int reps, double* gbs);
 /* Tile boundaries (world + 1 ints, bounds[0] = 0, bounds[world] = H): rank r renders rows
  * [bounds[r], bounds[r + 1]).  Equal heights by default; every rank must install the same bounds
  * before the same frame.  Rows through the hole and the disk cost more than sky rows, so a caller
