@@ -64,6 +64,8 @@ SIGNATURES = {
     "bhr_peer_attach": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "bhr_render_tiled_peer": (C.c_int, [_P, C.POINTER(BhrCamera), C.c_uint32, _P, _P]),
     "bhr_peer_detach": (C.c_int, [_P]),
+    "bhr_render_tiled_peer_async": (C.c_int, [_P, C.POINTER(BhrCamera), C.c_uint32, _P, _P]),
+    "bhr_peer_wait_frame": (C.c_int, [_P, C.c_int]),
     "bhr_peer_set_distributed_egress": (C.c_int, [_P, C.c_int]),
     "bhr_peer_probe_read": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "bhr_peer_set_tiles": (C.c_int, [_P, C.POINTER(C.c_int)]),

@@ -118,6 +118,8 @@ struct bhr_ctx {
     int* peer_host_err;                // host-mapped word a wait kernel writes when it gives up (peer.cu)
     double peer_timeout_ms;
     cudaEvent_t copy_done; int copy_pending;
+    // pipelined tiled frames (peer.cu): completion events of the last four frames, "my egress copy has read the final buffers"
+    cudaEvent_t tiled_ev[4]; cudaEvent_t tiled_copy_done; int tiled_copy_pending;
     // synchronous frames finished in row bands (api.cu): pieces per side of the photon-ring band (0 = off),
     // completion event per band, and "this launch continues a frame: keep the RK4 step total"
     int sync_bands; double sync_min_bytes, sync_extend; cudaEvent_t band_ev[12]; int keep_step_total;

@@ -9,13 +9,17 @@
 //   stage 2   vertical bloom pass: halo rows are loaded straight from the neighbours' H-blurred
 //             buffers (bloom_v_kernel's row_src table); flare parameters reduced on the device;
 //             composite: finished rows are stored straight into rank 0's final buffers
-//   publish   "my rows of frame s are in place" -> every rank
+//   publish   "my V pass of frame s is done" and "my rows of frame s are in place" -> every rank
 //   rank 0    waits for all tiles, copies the frame to the host, publishes "consumed s"
 //   (distributed egress: each rank copies its own rows into a shared, page-locked host frame over
 //    its own PCIe link instead of storing them into rank 0's HBM; rank 0 only waits)
-// Back-pressure: a rank starts frame s + 1 (overwrites its H-blurred rows) only when every rank has
-// finished frame s, and touches rank 0's final buffers / the host frame only when rank 0's caller
-// has come back for frame s + 1 (i.e. is done with frame s).
+// Back-pressure: a rank starts frame s + 1 (overwrites its H-blurred rows) only when every rank's V
+// pass of frame s is done, and touches rank 0's final buffers / the host frame only when rank 0's
+// caller has come back for frame s + 1 (i.e. is done with frame s).
+// Pipelined frames (bhr_render_tiled_peer_async, distributed egress only): the egress copies and
+// their flags run on the copy stream, so the rows of frame s leave over PCIe while frame s + 1 is
+// ray marched; frames alternate between TWO host frames, the caller collects frame s - 1
+// (bhr_peer_wait_frame) after it has enqueued frame s, and "consumed" lags by two frames.
 // Flags live in the memory of the rank that waits on them, so spinning is local.
 #include "common.cuh"
 
@@ -24,7 +28,8 @@ struct PeerSync {
     unsigned tile_done[16];      // [r] = s: rank r's rows of frame s are stored in rank 0's final buffers
     unsigned consumed;           // = s: rank 0 has copied frame s out of its final buffers
     unsigned poison;             // = s: some rank failed while frame s was in flight; waits for frames <= s give up
-    unsigned pad[30];
+    unsigned v_done[16];         // [r] = s: rank r's V pass of frame s no longer reads anybody's H-blurred rows
+    unsigned pad[14];
     double flare_part[16][3];
 };
 // A wait never spins for ever: if a flag does not arrive within the budget (a rank died, raised, or
@@ -44,7 +49,7 @@ __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// thread r publishes to rank r: field 0 = h_ready (+ flare partial sums), 1 = tile_done, 2 = consumed
+// thread r publishes to rank r: field 0 = h_ready (+ flare partial sums), 1 = tile_done, 2 = consumed, 4 = v_done, 3 = poison
 __global__ void peer_publish_kernel(PeerSync* const* __restrict__ peers, int rank, int world, const double* __restrict__ sums,
                                     unsigned serial, int field) {
     const int r = threadIdx.x;
@@ -60,11 +65,15 @@ __global__ void peer_publish_kernel(PeerSync* const* __restrict__ peers, int ran
     } else if (field == 2) {
         __threadfence_system();
         st_release_sys(&p->consumed, serial);
+    } else if (field == 4) {
+        __threadfence_system();
+        st_release_sys(&p->v_done[rank], serial);
     } else {
         // poison frame `serial`: this rank cannot finish it.  Its flags are published as well so that
         // nobody waits for it on this frame.
         st_release_sys(&p->poison, serial);
         st_release_sys(&p->h_ready[rank], serial);
+        st_release_sys(&p->v_done[rank], serial);
         st_release_sys(&p->tile_done[rank], serial);
         if (rank == 0) st_release_sys(&p->consumed, serial);
     }
@@ -103,9 +112,9 @@ static void tile_rows(int H, int world, int rank, int* r0, int* r1) {   // == di
     *r1 = *r0 + base + (rank < extra ? 1 : 0);
 }
 
-static int launch_wait(bhr_ctx* ctx, const unsigned* flags, int n, unsigned serial) {
+static int launch_wait(bhr_ctx* ctx, const unsigned* flags, int n, unsigned serial, cudaStream_t stream = nullptr) {
     const unsigned long long budget = (unsigned long long)(ctx->peer_timeout_ms > 0 ? ctx->peer_timeout_ms : 20000.0) * 1000000ull;
-    peer_wait_kernel<<<1, 32, 0, ctx->stream>>>(flags, n, serial, &ctx->peer_sync_own->poison, budget, ctx->peer_host_err);
+    peer_wait_kernel<<<1, 32, 0, stream ? stream : ctx->stream>>>(flags, n, serial, &ctx->peer_sync_own->poison, budget, ctx->peer_host_err);
     ++ctx->launches;
     BHR_CUDA(ctx, cudaGetLastError());
     return BHR_OK;
@@ -203,17 +212,18 @@ static int wait_consumed(bhr_ctx* ctx) {     // before the composite stores into
     return BHR_OK;
 }
 
-static int render_tiled_peer_body(bhr_ctx* ctx, const bhr_camera* cam, uint32_t flags, float* out_f32, uint8_t* out_u8, unsigned s);
+static int render_tiled_peer_body(bhr_ctx* ctx, const bhr_camera* cam, uint32_t flags, float* out_f32, uint8_t* out_u8, unsigned s,
+                                  bool pipelined);
 
-
-extern "C" int bhr_render_tiled_peer(bhr_ctx* ctx, const bhr_camera* cam, uint32_t flags, float* out_f32, uint8_t* out_u8) {
-    BhrDeviceGuard device_guard_(ctx);
+static int render_tiled_peer_entry(bhr_ctx* ctx, const bhr_camera* cam, uint32_t flags, float* out_f32, uint8_t* out_u8, bool pipelined) {
     if (!ctx || !cam) return BHR_ERR_INVALID;
     if (!ctx->peer_world) BHR_FAIL(ctx, BHR_ERR_STATE, "bhr_peer_attach has not run");
     int rc = peer_check_error(ctx);                  // a wait of an earlier frame gave up: the ranks are out of step
     if (rc) return rc;
+    if (pipelined && !((out_f32 || out_u8) && ctx->peer_distributed))
+        BHR_FAIL(ctx, BHR_ERR_STATE, "pipelined tiled frames need a host frame and distributed egress (bhr_peer_set_distributed_egress)");
     const unsigned s = ++ctx->peer_serial;
-    rc = render_tiled_peer_body(ctx, cam, flags, out_f32, out_u8, s);
+    rc = render_tiled_peer_body(ctx, cam, flags, out_f32, out_u8, s, pipelined);
     if (rc) {
         // this rank cannot finish frame s: poison it so that every peer's waits drain instead of spinning
         // (their frame is garbage and they report BHR_ERR_STATE); keep our own error message
@@ -225,21 +235,59 @@ extern "C" int bhr_render_tiled_peer(bhr_ctx* ctx, const bhr_camera* cam, uint32
     return BHR_OK;
 }
 
-static int render_tiled_peer_body(bhr_ctx* ctx, const bhr_camera* cam, uint32_t flags, float* out_f32, uint8_t* out_u8, unsigned s) {
+extern "C" int bhr_render_tiled_peer(bhr_ctx* ctx, const bhr_camera* cam, uint32_t flags, float* out_f32, uint8_t* out_u8) {
+    BhrDeviceGuard device_guard_(ctx);
+    return render_tiled_peer_entry(ctx, cam, flags, out_f32, out_u8, false);
+}
+
+// The same frame without the final synchronisation on rank 0 and with the egress on the copy stream.  Consecutive
+// calls must alternate between two host frames; bhr_peer_wait_frame(ctx, 1) after the call for frame s returns when
+// frame s - 1 is complete in its host frame (rank 0: every rank's rows; other ranks: their own rows).  Do not mix
+// with bhr_render_tiled_peer on the same context without a bhr_peer_wait_frame(ctx, 0) in between.
+extern "C" int bhr_render_tiled_peer_async(bhr_ctx* ctx, const bhr_camera* cam, uint32_t flags, float* out_f32, uint8_t* out_u8) {
+    BhrDeviceGuard device_guard_(ctx);
+    return render_tiled_peer_entry(ctx, cam, flags, out_f32, out_u8, true);
+}
+
+extern "C" int bhr_peer_wait_frame(bhr_ctx* ctx, int back) {
+    BhrDeviceGuard device_guard_(ctx);
+    if (!ctx || back < 0 || back > 2) return BHR_ERR_INVALID;
+    if (!ctx->peer_world) BHR_FAIL(ctx, BHR_ERR_STATE, "bhr_peer_attach has not run");
+    if ((unsigned)back >= ctx->peer_serial) return BHR_OK;                 // no such frame yet
+    const unsigned s = ctx->peer_serial - (unsigned)back;
+    if (!ctx->tiled_ev[s & 3]) BHR_FAIL(ctx, BHR_ERR_STATE, "frame %u was not enqueued with bhr_render_tiled_peer_async", s);
+    BHR_CUDA(ctx, cudaEventSynchronize(ctx->tiled_ev[s & 3]));
+    return peer_check_error(ctx);
+}
+
+static int render_tiled_peer_body(bhr_ctx* ctx, const bhr_camera* cam, uint32_t flags, float* out_f32, uint8_t* out_u8, unsigned s,
+                                  bool pipelined) {
     const int rank = ctx->peer_rank, world = ctx->peer_world;
     PeerSync* mine = ctx->peer_sync_own;
     // distributed egress: every rank copies its own rows into the (shared, page-locked) host frame
     const bool own_egress = rank != 0 && (out_f32 || out_u8);
     const bool host_out = out_f32 || out_u8;
     const int row0 = ctx->peer_bounds[rank], row1 = ctx->peer_bounds[rank + 1];
+    const unsigned lag = pipelined ? 2u : 1u;        // the host frame of frame s last held frame s - lag
     int rc;
-    if (rank == 0) {
-        // the caller is back for another frame: it is done with frame s - 1 (host frame / final buffers)
-        peer_publish_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_peer_sync, rank, world, nullptr, s - 1, 2);
+    cudaStream_t es = ctx->stream;                   // where the egress copies and their flags run
+    if (pipelined) {
+        if (!ctx->copy_stream) BHR_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        if (!ctx->tiled_copy_done) BHR_CUDA(ctx, cudaEventCreateWithFlags(&ctx->tiled_copy_done, cudaEventDisableTiming));
+        if (!ctx->frame_done) BHR_CUDA(ctx, cudaEventCreateWithFlags(&ctx->frame_done, cudaEventDisableTiming));
+        for (int k = 0; k < 4; ++k)
+            if (!ctx->tiled_ev[k]) BHR_CUDA(ctx, cudaEventCreateWithFlags(&ctx->tiled_ev[k], cudaEventDisableTiming));
+        es = ctx->copy_stream;
+        // the host runs at most two frames ahead of this rank's egress
+        if (s > 2) BHR_CUDA(ctx, cudaEventSynchronize(ctx->tiled_ev[(s - 2) & 3]));
+    }
+    if (rank == 0 && s >= lag) {
+        // the caller is back for another frame: it is done with frame s - lag (host frame / final buffers)
+        peer_publish_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_peer_sync, rank, world, nullptr, s - lag, 2);
         ++ctx->launches;
     }
-    // every rank has finished frame s - 1 (its V pass no longer reads my H-blurred rows)
-    rc = launch_wait(ctx, mine->tile_done, world, s - 1);
+    // every rank's V pass of frame s - 1 is done (it no longer reads my H-blurred rows)
+    rc = launch_wait(ctx, mine->v_done, world, s - 1);
     if (rc) return rc;
     rc = bhr_render_rows_stage1(ctx, cam, flags, row0, row1);
     if (rc) return rc;
@@ -256,6 +304,11 @@ static int render_tiled_peer_body(bhr_ctx* ctx, const bhr_camera* cam, uint32_t 
         rc = bhr_launch_flare_params(ctx, &mine->flare_part[0][0], world, ctx->d_flare_params);
         if (rc) return rc;
     }
+    // the egress copy of the previous pipelined frame has read my final buffers
+    if (ctx->tiled_copy_pending) {
+        BHR_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->tiled_copy_done, 0));
+        ctx->tiled_copy_pending = 0;
+    }
     bhr_post_peer peer;
     peer.row_src = ctx->d_row_src;
     peer.final_f32 = own_egress ? nullptr : ctx->peer_final_f32[0];
@@ -267,29 +320,45 @@ static int render_tiled_peer_body(bhr_ctx* ctx, const bhr_camera* cam, uint32_t 
     if (rc) return rc;
     if (ctx->stage_timing) BHR_CUDA(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
     ctx->ev_valid = ctx->stage_timing;
+    peer_publish_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_peer_sync, rank, world, nullptr, s, 4);
+    ++ctx->launches;
+    if (pipelined) {
+        BHR_CUDA(ctx, cudaEventRecord(ctx->frame_done, ctx->stream));
+        BHR_CUDA(ctx, cudaStreamWaitEvent(es, ctx->frame_done, 0));
+    }
     const size_t row3 = (size_t)ctx->W * 3;
     if (own_egress) {
-        rc = wait_consumed(ctx);                 // the host frame still holds s - 1 until rank 0's caller returns for more
-        if (rc) return rc;
+        // the host frame still holds frame s - lag until rank 0's caller has come back for more
+        if (s >= lag) {
+            rc = launch_wait(ctx, &mine->consumed, 1, s - lag, es);
+            if (rc) return rc;
+        }
         if (out_f32) BHR_CUDA(ctx, cudaMemcpyAsync(out_f32 + row0 * row3, ctx->final_f32 + row0 * row3,
-                                                   (row1 - row0) * row3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+                                                   (row1 - row0) * row3 * sizeof(float), cudaMemcpyDeviceToHost, es));
         if (out_u8) BHR_CUDA(ctx, cudaMemcpyAsync(out_u8 + row0 * row3, ctx->final_u8 + row0 * row3, (row1 - row0) * row3,
-                                                  cudaMemcpyDeviceToHost, ctx->stream));
+                                                  cudaMemcpyDeviceToHost, es));
     }
-    peer_publish_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_peer_sync, rank, world, nullptr, s, 1);
-    ++ctx->launches;
+    if (rank != 0) {
+        peer_publish_kernel<<<1, 32, 0, es>>>(ctx->d_peer_sync, rank, world, nullptr, s, 1);
+        ++ctx->launches;
+    }
     BHR_CUDA(ctx, cudaGetLastError());
     if (rank == 0) {
         const bool distributed = host_out && ctx->peer_distributed;
         if (distributed) {
             // my own rows go out right away; the other ranks' rows arrive over their own links
             if (out_f32) BHR_CUDA(ctx, cudaMemcpyAsync(out_f32 + row0 * row3, ctx->final_f32 + row0 * row3,
-                                                       (row1 - row0) * row3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+                                                       (row1 - row0) * row3 * sizeof(float), cudaMemcpyDeviceToHost, es));
             if (out_u8) BHR_CUDA(ctx, cudaMemcpyAsync(out_u8 + row0 * row3, ctx->final_u8 + row0 * row3, (row1 - row0) * row3,
-                                                      cudaMemcpyDeviceToHost, ctx->stream));
-            rc = launch_wait(ctx, mine->tile_done, world, s);
+                                                      cudaMemcpyDeviceToHost, es));
+            peer_publish_kernel<<<1, 32, 0, es>>>(ctx->d_peer_sync, rank, world, nullptr, s, 1);
+            ++ctx->launches;
+            if (pipelined) { BHR_CUDA(ctx, cudaEventRecord(ctx->tiled_copy_done, es)); ctx->tiled_copy_pending = 1; }
+            rc = launch_wait(ctx, mine->tile_done, world, s, es);
             if (rc) return rc;
         } else {
+            peer_publish_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_peer_sync, rank, world, nullptr, s, 1);
+            ++ctx->launches;
             rc = launch_wait(ctx, mine->tile_done, world, s);
             if (rc) return rc;
             const size_t n3 = (size_t)ctx->H * row3;
@@ -297,10 +366,18 @@ static int render_tiled_peer_body(bhr_ctx* ctx, const bhr_camera* cam, uint32_t 
             if (out_u8) BHR_CUDA(ctx, cudaMemcpyAsync(out_u8, ctx->final_u8, n3, cudaMemcpyDeviceToHost, ctx->stream));
         }
         BHR_CUDA(ctx, cudaGetLastError());
+        if (pipelined) {
+            BHR_CUDA(ctx, cudaEventRecord(ctx->tiled_ev[s & 3], es));
+            return BHR_OK;
+        }
         if (host_out) {
             BHR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
             return peer_check_error(ctx);
         }
+    } else if (pipelined) {
+        BHR_CUDA(ctx, cudaEventRecord(ctx->tiled_copy_done, es));
+        ctx->tiled_copy_pending = 1;
+        BHR_CUDA(ctx, cudaEventRecord(ctx->tiled_ev[s & 3], es));
     }
     return BHR_OK;
 }
@@ -346,6 +423,7 @@ extern "C" int bhr_peer_detach(bhr_ctx* ctx) {
     if (!ctx) return BHR_ERR_INVALID;
     if (!ctx->peer_world) return BHR_OK;
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     for (int r = 0; r < ctx->peer_world; ++r) {
         if (r == ctx->peer_rank) continue;
         cudaIpcCloseMemHandle(ctx->peer_hblur[r]); cudaIpcCloseMemHandle(ctx->peer_final_f32[r]);

@@ -209,15 +209,21 @@ def render_tiled(renderer, cam_pos, fov, frame=0, skip_differentials=False, skip
 
 
 def balance_tiles(renderer, cam_pos, fov, rank, world_size, group=None, post_cost_per_pixel=10.0,
-                  skip_differentials=False):
+                  skip_differentials=False, refine=2):
     """Cost-balanced tile boundaries for `render_tiled` / `render_tiled_peer`: rows through the hole
     and the disk cost more than sky rows.  Every rank traces its equal-height tile once with the
     per-pixel step counts on, reduces them to RK4 evaluations per row on the device
     (bhr_row_costs), the per-row costs are all-gathered, and every rank derives the same
     boundaries (`balanced_bounds`; cost of a row = its RK4 evaluations + `post_cost_per_pixel`
     step-equivalents per pixel for bloom / composite / egress).  For a camera path the boundaries
-    of one frame serve its neighbours (the cost profile moves slowly).  Returns the bounds list;
-    with peers attached it is installed in the library as well."""
+    of one frame serve its neighbours (the cost profile moves slowly).
+    `refine` rounds of calibration follow: an RK4 evaluation does not cost the same everywhere (rays of
+    the photon ring run in the strict integrator at about three times the cost, and a tile that holds
+    them has the latency of a strict batch as its floor), so every rank times stage 1 on its tile, the
+    times are all-gathered, the row costs of each tile are scaled by (measured time / modelled cost)
+    and the bounds are cut again.  Returns the bounds list; with peers attached it is installed in the
+    library as well."""
+    import time
     import ctypes as C
     H, W = renderer.height, renderer.width
     eq = equal_bounds(H, world_size)
@@ -235,6 +241,31 @@ def balance_tiles(renderer, cam_pos, fov, rank, world_size, group=None, post_cos
         everyone = [costs.tolist()]
     rows = np.concatenate([np.asarray(e, dtype=np.float64) for e in everyone]) + post_cost_per_pixel * W
     bounds = balanced_bounds(rows, world_size, min_rows=8)
+    def stage1_seconds(bounds):
+        a, b = bounds[rank], bounds[rank + 1]
+        best = float("inf")
+        for _rep in range(3):                       # (the first repetition warms the tile's working set)
+            renderer.synchronize()
+            t0 = time.perf_counter()
+            L.check(ctx, lib.bhr_render_rows_stage1(ctx, C.byref(cam), flags, a, b))
+            renderer.synchronize()
+            best = min(best, time.perf_counter() - t0)
+        times = [None] * world_size
+        dist.all_gather_object(times, best, group=group)
+        return times
+
+    for it in range(refine + 1 if world_size > 1 else 0):
+        times = stage1_seconds(bounds)
+        renderer._tile_stage1_ms = [round(1e3 * t, 4) for t in times]     # stage 1 per rank for `bounds` (diagnostics)
+        if it == refine:
+            break
+        scaled = rows.copy()
+        for r in range(world_size):
+            model = rows[bounds[r]:bounds[r + 1]].sum()
+            if model > 0:
+                scaled[bounds[r]:bounds[r + 1]] *= times[r] / model
+        rows = scaled
+        bounds = balanced_bounds(rows, world_size, min_rows=8)
     if renderer.__dict__.get("_peer_world"):
         arr = (C.c_int * (world_size + 1))(*bounds)
         L.check(ctx, lib.bhr_peer_set_tiles(ctx, arr))
@@ -285,7 +316,11 @@ def attach_shared_frame(renderer, rank, world_size, group=None, dtype=np.uint8):
     dist.barrier(group=group)
     if rank == 0:
         shm.unlink()                      # the mappings keep it alive; nothing is left behind in /dev/shm
-    renderer._shared_frame, renderer._shared_shm = frame, shm
+    if renderer.__dict__.get("_shared_frame") is None:
+        renderer._shared_frame, renderer._shared_shm = frame, shm
+    # every shared frame of this renderer: pipelined tiled frames alternate between the first two
+    renderer.__dict__.setdefault("_shared_frames", []).append(frame)
+    renderer.__dict__.setdefault("_shared_shms", []).append(shm)
     return frame
 
 
@@ -317,3 +352,31 @@ def render_tiled_peer(renderer, cam_pos, fov, frame=0, skip_differentials=False,
             f32 = out.ctypes.data
     L.check(renderer._ctx, renderer._lib.bhr_render_tiled_peer(renderer._ctx, C.byref(cam), flags, f32, u8))
     return out if renderer._peer_rank == 0 else None
+
+
+def render_tiled_peer_async(renderer, cam_pos, fov, frame=0, skip_differentials=False, skip_bloom=False):
+    """Pipelined variant of `render_tiled_peer` (needs TWO shared host frames: call `attach_shared_frame` twice):
+    enqueues the frame and returns; the rows leave every GPU on its copy stream while the next frame is ray
+    marched.  Frames alternate between the two shared frames.  `wait_tiled_frame(renderer, back=1)` after the call
+    for frame s returns frame s - 1 on rank 0; finish a sequence with `wait_tiled_frame(renderer, back=0)`."""
+    import ctypes as C
+    frames = renderer.__dict__.get("_shared_frames", [])
+    assert len(frames) >= 2, "pipelined tiled frames alternate between two shared host frames"
+    k = renderer.__dict__.get("_tiled_async_count", 0)
+    out = frames[k & 1]
+    renderer._tiled_async_count = k + 1
+    cam = renderer._camera(cam_pos, fov, frame)
+    flags = renderer._flags(skip_differentials, skip_bloom)
+    f32 = out.ctypes.data if out.dtype == np.float32 else None
+    u8 = out.ctypes.data if out.dtype == np.uint8 else None
+    L.check(renderer._ctx, renderer._lib.bhr_render_tiled_peer_async(renderer._ctx, C.byref(cam), flags, f32, u8))
+
+
+def wait_tiled_frame(renderer, back=1):
+    """Block until the pipelined frame `back` calls ago is complete; rank 0 gets its host frame (valid until the next
+    `render_tiled_peer_async` but one), the other ranks None.  Returns None when there is no such frame yet."""
+    k = renderer.__dict__.get("_tiled_async_count", 0)
+    L.check(renderer._ctx, renderer._lib.bhr_peer_wait_frame(renderer._ctx, int(back)))
+    if k - 1 - back < 0 or renderer._peer_rank != 0:
+        return None
+    return renderer._shared_frames[(k - 1 - back) & 1]

@@ -200,6 +200,13 @@ int bhr_peer_export(bhr_ctx* ctx, bhr_ipc_handle out[4]);
 int bhr_peer_attach(bhr_ctx* ctx, int rank, int world, const bhr_ipc_handle* all);
 int bhr_render_tiled_peer(bhr_ctx* ctx, const bhr_camera* cam, uint32_t flags, float* out_f32, uint8_t* out_u8);
 int bhr_peer_set_distributed_egress(bhr_ctx* ctx, int enabled);   /* all ranks, before the first frame */
+/* Pipelined row-tiled frames (distributed egress only): the call returns once frame s is enqueued; the egress copies
+ * and their flags run on the context's copy stream, so the rows of frame s leave over PCIe while frame s + 1 is ray
+ * marched.  Consecutive calls must alternate between TWO host frames.  bhr_peer_wait_frame(ctx, back) blocks until
+ * frame (latest - back) is complete in its host frame (rank 0: every rank's rows; other ranks: their own rows) and
+ * reports a failed / timed-out peer.  Typical loop: async(s); wait_frame(1) -> frame s - 1; ...; wait_frame(0). */
+int bhr_render_tiled_peer_async(bhr_ctx* ctx, const bhr_camera* cam, uint32_t flags, float* out_f32, uint8_t* out_u8);
+int bhr_peer_wait_frame(bhr_ctx* ctx, int back);
 /* measurement hook: GB/s at which this rank reads rank `peer`'s H-blurred layer through the peer mapping (the halo
  * pull's access pattern); above PCIe's 64 GB/s the mapping is NVLink */
 int bhr_peer_probe_read(bhr_ctx* ctx, int peer, int reps, double* gbs);

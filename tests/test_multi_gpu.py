@@ -112,6 +112,28 @@ def _peer_worker(rank, world, port, out_dir):
         np.save(os.path.join(out_dir, "balanced_all.npy"), np.stack(bal))
         np.save(os.path.join(out_dir, "bounds.npy"), np.array(bounds))
     dist.barrier()
+    # pipelined frames: egress on the copy streams, two shared host frames, the caller collects frame s - 1 after
+    # it has enqueued frame s (two passes over the cameras: the frame serials wrap around the four completion events)
+    from black_hole_renderer_b200.dist import render_tiled_peer_async, wait_tiled_frame
+    attach_shared_frame(r, rank, world)
+    piped = []
+    seq = cams + cams[::-1] + cams
+    for c in seq:
+        render_tiled_peer_async(r, c, 90)
+        f = wait_tiled_frame(r, back=1)
+        if rank == 0 and f is not None:
+            piped.append(f.copy())
+    f = wait_tiled_frame(r, back=0)
+    if rank == 0:
+        piped.append(f.copy())
+        assert len(piped) == len(seq)
+        np.save(os.path.join(out_dir, "pipelined_all.npy"), np.stack(piped))
+    dist.barrier()
+    # ... and the synchronous call still works afterwards
+    f = render_tiled_peer(r, cams[1], 90)
+    if rank == 0:
+        np.save(os.path.join(out_dir, "after_pipelined.npy"), f.copy())
+    dist.barrier()
     r.close()
     dist.destroy_process_group()
 
@@ -192,6 +214,10 @@ def test_peer_memory_tiled_frame_equals_single_gpu(tmp_path, world):
     assert bounds[0] == 0 and bounds[-1] == 360 and len(bounds) == world + 1 and (np.diff(bounds) >= 8).all()
     d = np.abs(bal.astype(int) - single.astype(int))
     assert d.max() <= 1 and (d.max(axis=-1) > 0).mean() < 1e-3
+    # pipelined frames (egress on the copy streams, two host frames) are the same frames, in order
+    piped = np.load(tmp_path / "pipelined_all.npy")
+    assert np.array_equal(piped, np.concatenate([bal, bal[::-1], bal]))
+    assert np.array_equal(np.load(tmp_path / "after_pipelined.npy"), bal[1])
 
 
 @pytest.mark.parametrize("world", [2, 4])
