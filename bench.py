@@ -368,6 +368,16 @@ def tiled_4k(Renderer, sky, rank, world, local, dist, torch, frames=8):
                                    "path": "balanced tiles + distributed egress: every rank copies its own rows into one shared, "
                                            "page-locked host frame over its own PCIe link"}
     compare("peer_balanced_egress", frame)
+    # where a tiled frame's time goes on every rank: the library's stage events around one more frame
+    # (ray march, H pass, [h_ready barrier + halo pull +] V pass + composite, flare; total = first to last event)
+    r.set_option("stage_timing", 1)
+    D.render_tiled_peer(r, POV, FOV)
+    torch.cuda.synchronize()
+    st = r.last_stage_ms()
+    r.set_option("stage_timing", 0)
+    stages = [None] * world
+    dist.all_gather_object(stages, {k: round(float(v), 4) for k, v in st.items()})
+    out["peer_balanced_egress"]["stage_ms_per_rank"] = stages
     # pipelined: a second shared host frame; the call for frame s returns frame s - 1
     D.attach_shared_frame(r, rank, world)
 
