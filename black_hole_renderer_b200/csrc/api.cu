@@ -172,6 +172,12 @@ extern "C" int bhr_set_option(bhr_ctx* ctx, const char* key, double value) {
     if (ctx && !strcmp(key, "bloom_generic")) { ctx->bloom_generic = (int)value; return BHR_OK; }
     if (ctx && !strcmp(key, "keep_blur")) { ctx->keep_blur = (int)value; return BHR_OK; }
     if (ctx && !strcmp(key, "timeline")) { ctx->timeline = (int)value; return BHR_OK; }
+    if (ctx && !strcmp(key, "raymarch_pair")) {          // 0 = one ray per thread; 384 / 448 / 512 = threads per block, two rays each
+        const int v = (int)value;
+        if (v != 0 && v != 384 && v != 448 && v != 512) BHR_FAIL(ctx, BHR_ERR_INVALID, "raymarch_pair must be 0, 384, 448 or 512");
+        ctx->raymarch_pair = v;
+        return BHR_OK;
+    }
     if (ctx && !strcmp(key, "background_blocks_per_sm")) {      // resident blocks of the packed background kernel (experiments)
         if (value < 1) BHR_FAIL(ctx, BHR_ERR_INVALID, "background_blocks_per_sm must be >= 1");
         ctx->bg_blocks_per_sm = (int)value;

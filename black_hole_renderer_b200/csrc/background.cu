@@ -70,14 +70,10 @@ __device__ __forceinline__ void load_tables(unsigned char* smem /* 16-byte align
 // lattice indices modulo 256 (MAGIC + n has the integer pattern 0x4B400000 + n for |n| < 2^22)
 __device__ __forceinline__ void floor2(const Consts& K, const float2 v, float2& f, unsigned& bits_a, unsigned& bits_b) {
     const float MAGIC = 12582912.0f;                       // 1.5 * 2^23
-#ifdef BHR_BG_XU_FLOOR
-    f = make_float2(floorf(v.x), floorf(v.y));             // FRND + F2I on the (idle) XU pipe instead of two FFMA2
-    bits_a = (unsigned)(int)f.x; bits_b = (unsigned)(int)f.y;
-#else
+    // (FRND + F2I on the XU pipe instead of these two FFMA2 was measured: no difference)
     const float2 r = __ffma2_rd(v, K.one, k2(MAGIC));      // rounded DOWN: MAGIC + floor(v)
     bits_a = __float_as_uint(r.x); bits_b = __float_as_uint(r.y);
     f = s2(r, k2(MAGIC));
-#endif
 }
 
 // gradient index of one corner of one lane: perm[ii + o + perm[jj + p + pk]] (all offsets already added in)
@@ -180,10 +176,7 @@ __global__ void background_rows_kernel(float* __restrict__ rows, int n_r, float 
 // A thread owns two neighbouring texels of a row; blocks are persistent and walk the texel pairs grid-stride.
 // The cos / sin of the Keplerian-rotated angle feed noise coordinates scaled by up to 800, so they are evaluated
 // in double and rounded once (the oracle's ideal-libm convention).
-#ifndef BHR_BG_MINBLOCKS
-#define BHR_BG_MINBLOCKS 2
-#endif
-__global__ void __launch_bounds__(256, BHR_BG_MINBLOCKS) background_kernel(float* __restrict__ comp, const float* __restrict__ rows, int n_r, int n_phi,
+__global__ void __launch_bounds__(256, 2) background_kernel(float* __restrict__ comp, const float* __restrict__ rows, int n_r, int n_phi,
                                                          int az_freq, float t, const Consts K) {
     __shared__ __align__(16) unsigned char stab[kTableBytes];
     Tables T;

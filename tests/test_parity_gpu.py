@@ -587,6 +587,25 @@ def test_planar_integrator_option_stays_inside_the_north_star_gate():
     assert abs(int(steps.sum()) - ref["total_steps"]) <= 1e-3 * ref["total_steps"]
 
 
+def test_two_rays_per_thread_option_gives_the_same_pixels():
+    """Option raymarch_pair (trace_pair: two adjacent pixels in the two lanes of every f32x2 register, every FP32
+    instruction of the step packed).  Measured slower than one ray per thread, kept as an A/B option:
+    the same per-lane operations, so the frame, the class map and every ray's step count are identical."""
+    for res in ((333, 187), "fhd"):
+        r, sky, tex, pov, fov, W, H = _scene(res)
+        a = r.render(pov, fov, aux=True)
+        cls_a, steps_a = r.last_aux()
+        total = r.last_total_steps()
+        for threads in (512, 384):
+            r.set_option("raymarch_pair", threads)
+            b = r.render(pov, fov, aux=True)
+            cls_b, steps_b = r.last_aux()
+            assert np.array_equal(a, b) and np.array_equal(cls_a, cls_b) and np.array_equal(steps_a, steps_b), (res, threads)
+            assert r.last_total_steps() == total
+        r.set_option("raymarch_pair", 0)
+        r.close()
+
+
 def test_physics_capture_iff_subcritical_impact_parameter():
     """Physics known-answer test through the C-ABI: a ray ends in the horizon iff its
     impact parameter at infinity b = L / sqrt(1 - L^2 / r_cam^3) is below 3 sqrt(3) / 2, for every
