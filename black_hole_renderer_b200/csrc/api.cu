@@ -172,6 +172,10 @@ extern "C" int bhr_set_option(bhr_ctx* ctx, const char* key, double value) {
     if (ctx && !strcmp(key, "bloom_generic")) { ctx->bloom_generic = (int)value; return BHR_OK; }
     if (ctx && !strcmp(key, "keep_blur")) { ctx->keep_blur = (int)value; return BHR_OK; }
     if (ctx && !strcmp(key, "timeline")) { ctx->timeline = (int)value; return BHR_OK; }
+    if (ctx && !strcmp(key, "bloom_h_p")) {               // pixels per lane of the TMA H pass: 0 = by width, 5, 10
+        ctx->bloom_h_P_option = (int)value;
+        return bhr_setup_bloom_tma(ctx);
+    }
     if (ctx && !strcmp(key, "raymarch_pair")) {          // 0 = one ray per thread; 384 / 448 / 512 = threads per block, two rays each
         const int v = (int)value;
         if (v != 0 && v != 384 && v != 448 && v != 512) BHR_FAIL(ctx, BHR_ERR_INVALID, "raymarch_pair must be 0, 384, 448 or 512");

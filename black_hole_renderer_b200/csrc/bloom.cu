@@ -67,7 +67,6 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
 }
 
 __device__ __forceinline__ float2 splat2(float s) { return make_float2(s, s); }
-
 // The stencil of one thread: P packed outputs, `ntaps` taps.  `ld(base, k)` returns sample pair base + k of the
 // thread's window (k a compile-time offset, base advanced once per P taps, so every load is pointer + immediate);
 // `wsh[j]` is the weight of tap j.  Samples and weights are fetched one tap ahead of their use: a tap's new
@@ -127,7 +126,7 @@ struct HArgs {
 };
 
 template <int P>
-__global__ void __launch_bounds__(256, 2) bloom_h_tma_kernel(const __grid_constant__ CUtensorMap src_map, const HArgs a) {
+__global__ void __launch_bounds__(256, P <= 10 ? 3 : 2) bloom_h_tma_kernel(const __grid_constant__ CUtensorMap src_map, const HArgs a) {
     extern __shared__ __align__(128) unsigned char hsm[];
     constexpr int TX = 32 * P;
     // (the shuffle tells the compiler that the warp index is warp-uniform: the TMA operands derived from it then
@@ -465,8 +464,11 @@ int bhr_setup_bloom_tma(bhr_ctx* ctx) {
         return BHR_OK;
     }
     const PFN_encodeTiled enc = (PFN_encodeTiled)fn;
-    // H pass: P = 15 pixels per lane when the width is a multiple of 480 (fhd, 4K), else 5 (sd, hd)
-    ctx->bloom_h_P = (W % 480 == 0) ? 15 : 5;
+    // H pass: P = 15 pixels per lane when the width is a multiple of 480 (fhd, 4K), 10 for multiples of 320 (hd, sd:
+    // 14.4 vs 18.5 us at hd with P = 5; at fhd / 4K P = 10 with three blocks per SM is no faster than 15 with two), else 5
+    ctx->bloom_h_P = (W % 480 == 0) ? 15 : (W % 320 == 0) ? 10 : 5;
+    if (ctx->bloom_h_P_option == 10 && W % 320 == 0) ctx->bloom_h_P = 10;      // option "bloom_h_p": A/B
+    if (ctx->bloom_h_P_option == 5) ctx->bloom_h_P = 5;
     // (boxes start 16-byte aligned in global memory; + 1: the stencil reads one sample past its window)
     const int seg = 32 * ctx->bloom_h_P + R + (R + 3) / 4 * 4 + 1;
     ctx->bloom_h_nb = bhr_div_up(seg, 256);
@@ -489,9 +491,10 @@ int bhr_setup_bloom_tma(bhr_ctx* ctx) {
         const int per_sm_staged = bhr_div_up(n_tiles, ctx->num_sms), per_sm_unstaged = 2 * bhr_div_up(n_tiles, 2 * ctx->num_sms);
         ctx->bloom_v_staged = v_smem(ctx, false) > 112 * 1024 || per_sm_staged < per_sm_unstaged;
     }
-    const size_t hs = ctx->bloom_h_P == 15 ? h_smem<15>(ctx) : h_smem<5>(ctx), vs = v_smem(ctx, ctx->bloom_v_staged);
+    const size_t hs = h_smem<15>(ctx), vs = v_smem(ctx, ctx->bloom_v_staged);      // (h_smem does not depend on P but through segp)
     if (hs > 110 * 1024 || vs > 225 * 1024) return BHR_OK;
     if (ctx->bloom_h_P == 15) BHR_CUDA(ctx, cudaFuncSetAttribute(bloom_h_tma_kernel<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hs));
+    else if (ctx->bloom_h_P == 10) BHR_CUDA(ctx, cudaFuncSetAttribute(bloom_h_tma_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hs));
     else BHR_CUDA(ctx, cudaFuncSetAttribute(bloom_h_tma_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hs));
     if (ctx->bloom_v_staged) BHR_CUDA(ctx, cudaFuncSetAttribute(bloom_v_fused_kernel<V_P, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vs));
     else BHR_CUDA(ctx, cudaFuncSetAttribute(bloom_v_fused_kernel<V_P, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vs));
@@ -509,8 +512,10 @@ int bhr_launch_bloom_h_tma(bhr_ctx* ctx, int row0, int row1) {
     memcpy(&map, ctx->tmap_disk_row, 128);
     const int P = ctx->bloom_h_P;
     const int n_tasks = 3 * ((row1 - row0 + 1) / 2) * bhr_div_up(ctx->W, 32 * P);
-    const int grid = bhr_div_up(n_tasks, 8) < 2 * ctx->num_sms ? bhr_div_up(n_tasks, 8) : 2 * ctx->num_sms;
+    const int per_sm = P <= 10 ? 3 : 2;
+    const int grid = bhr_div_up(n_tasks, 8) < per_sm * ctx->num_sms ? bhr_div_up(n_tasks, 8) : per_sm * ctx->num_sms;
     if (P == 15) bloom_h_tma_kernel<15><<<grid, 256, h_smem<15>(ctx), ctx->stream>>>(map, a);
+    else if (P == 10) bloom_h_tma_kernel<10><<<grid, 256, h_smem<10>(ctx), ctx->stream>>>(map, a);
     else bloom_h_tma_kernel<5><<<grid, 256, h_smem<5>(ctx), ctx->stream>>>(map, a);
     ++ctx->launches;
     BHR_CUDA(ctx, cudaGetLastError());

@@ -124,6 +124,7 @@ struct bhr_ctx {
     // completion event per band, and "this launch continues a frame: keep the RK4 step total"
     int sync_bands; double sync_min_bytes, sync_extend; cudaEvent_t band_ev[12]; int keep_step_total;
     int strict_warps, band_box, planar, planar_attr_set;
+    int bloom_h_P_option;              // option "bloom_h_p": pixels per lane of the TMA H pass (0 = by width)
     int raymarch_pair;                 // option "raymarch_pair": threads per block of the two-rays-per-thread ray march (0 = one ray per thread)
     int timeline; unsigned long long* d_timeline;   // option "timeline": per-block timestamps of the persistent ray march
     unsigned long long launches;       // kernels this context has launched (bhr_launch_count)
