@@ -271,6 +271,9 @@ int bhr_setup_background(bhr_ctx* ctx) {
                                                                              ctx->cfg.r_disk_outer);
     BHR_CUDA(ctx, cudaGetLastError());
     BHR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    // the entity kernels may share the SMs with this kernel (option "entity_stream"): kernels whose shared-memory carve-outs
+    // differ cannot be resident on one SM together, so ask for a carve-out that has room for their blocks as well
+    BHR_CUDA(ctx, cudaFuncSetAttribute(background_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 50));
     int per_sm = 0;
     BHR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, background_kernel, 256, 0));
     ctx->bg_blocks_per_sm = per_sm < 1 ? 1 : per_sm;
@@ -280,7 +283,10 @@ int bhr_setup_background(bhr_ctx* ctx) {
 int bhr_launch_background(bhr_ctx* ctx, float t) {
     // persistent blocks (hash / gradient tables filled once each): as many as stay resident
     const int want = bhr_div_up(ctx->n_r * (ctx->n_phi / 2), 256);
-    const int cap = ctx->bg_blocks_per_sm * ctx->num_sms;
+    // With the entity stream on, ONE block per SM: the two blocks that fit hold the whole register file, and the entity
+    // kernels (FP64 / XU heavy, this one FP32 heavy) are to run beside it.  Alone that costs 0.330 instead of 0.307 ms,
+    // together with the entity layer 0.391 instead of 0.435 (tools/entity_overlap.py).
+    const int cap = (ctx->entity_stream_on ? 1 : ctx->bg_blocks_per_sm) * ctx->num_sms;
     Consts K;
     K.one = make_float2(1.0f, 1.0f); K.minus_one = make_float2(-1.0f, -1.0f); K.neg_zero = make_float2(-0.0f, -0.0f);
     background_kernel<<<want < cap ? want : cap, 256, 0, ctx->stream>>>(ctx->comp, ctx->bg_rows, ctx->n_r, ctx->n_phi, ctx->az_freq, t, K);

@@ -134,7 +134,7 @@ struct bhr_ctx {
     void* d_png_tables; unsigned int* d_png_staging; unsigned int* d_png_seg; unsigned long long* d_png_off;
     uint8_t* d_png_stream[BHR_FRAME_SLOTS]; int png_n_seg; size_t png_capacity;
     // the entity layer runs on its own stream next to the background kernel (texture.cu): FP64-bound beside FP32-bound
-    cudaStream_t ent_stream; cudaEvent_t bg_start_ev, ent_done_ev; int bg_start_armed, ent_pending, entity_stream_on;
+    cudaStream_t ent_stream; cudaEvent_t bg_start_ev, ent_done_ev; int bg_start_armed, ent_pending, entity_stream_on, entity_carveout_set;
     int ev_valid;
     float tint[3];
 };

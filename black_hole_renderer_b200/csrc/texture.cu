@@ -517,6 +517,11 @@ extern "C" int bhr_accumulate_entities(bhr_ctx* ctx, const bhr_entity* entities,
     }
     const size_t smem = (size_t)n * sizeof(RowEntity);
     if (smem > 200 * 1024) BHR_FAIL(ctx, BHR_ERR_INVALID, "too many entities (%d) for the per-row list", n);
+    if (ctx->entity_stream_on && !ctx->entity_carveout_set) {      // the same carve-out as the background kernel they run beside
+        BHR_CUDA(ctx, cudaFuncSetAttribute(entity_accumulate_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 50));
+        BHR_CUDA(ctx, cudaFuncSetAttribute(entity_coltab_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 50));
+        ctx->entity_carveout_set = 1;
+    }
     if (smem > 48 * 1024)
         BHR_CUDA(ctx, cudaFuncSetAttribute(entity_accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(bhr_div_up(ctx->n_phi, kEntCols), ctx->n_r);
