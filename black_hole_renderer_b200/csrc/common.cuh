@@ -211,4 +211,4 @@ int bhr_launch_bloom_h_tma(bhr_ctx* ctx, int row0, int row1);
 int bhr_launch_bloom_v_fused(bhr_ctx* ctx, uint32_t flags, int row0, int row1, const void* F_host, const void* F_dev,
                              const float* const* row_src, float* dst_f32, uint8_t* dst_u8);
 int bhr_launch_blur_only(bhr_ctx* ctx);
-int bhr_launch_png_encode(bhr_ctx* ctx, int slot);
+int bhr_launch_png_encode(bhr_ctx* ctx, int slot, cudaStream_t stream);

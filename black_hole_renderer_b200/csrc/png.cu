@@ -318,8 +318,8 @@ extern "C" int bhr_png_capacity(bhr_ctx* ctx, size_t* stream_bytes) {
     return BHR_OK;
 }
 
-// encode the current 8-bit frame (BHR_BUF_FINAL_U8) into slot's device stream; enqueued on the context's stream
-int bhr_launch_png_encode(bhr_ctx* ctx, int slot) {
+// encode the current 8-bit frame (BHR_BUF_FINAL_U8) into slot's device stream; enqueued on `stream`
+int bhr_launch_png_encode(bhr_ctx* ctx, int slot, cudaStream_t stream) {
     if (!ctx->d_png_tables) BHR_FAIL(ctx, BHR_ERR_STATE, "bhr_png_setup has not run");
     if (!ctx->d_png_stream[slot]) {
         BHR_CUDA(ctx, cudaMalloc(&ctx->d_png_stream[slot], ctx->png_capacity + sizeof(PngInfo)));
@@ -329,11 +329,11 @@ int bhr_launch_png_encode(bhr_ctx* ctx, int slot) {
     const size_t n_bytes = (size_t)ctx->H * (3 * (size_t)ctx->W + 1);
     const int n_seg = ctx->png_n_seg, n_blocks = bhr_div_up(n_seg, kEncWarps);
     PngBlockSums* block_sums = reinterpret_cast<PngBlockSums*>(ctx->d_png_off + n_blocks);
-    BHR_CUDA(ctx, cudaMemsetAsync(out, 0, ctx->png_capacity, ctx->stream));
-    png_encode_kernel<<<n_blocks, 32 * kEncWarps, 0, ctx->stream>>>(ctx->final_u8, 3 * ctx->W, (unsigned int)n_bytes, n_seg, (const PngTables*)ctx->d_png_tables,
+    BHR_CUDA(ctx, cudaMemsetAsync(out, 0, ctx->png_capacity, stream));
+    png_encode_kernel<<<n_blocks, 32 * kEncWarps, 0, stream>>>(ctx->final_u8, 3 * ctx->W, (unsigned int)n_bytes, n_seg, (const PngTables*)ctx->d_png_tables,
                                                                     ctx->d_png_staging, ctx->d_png_seg, block_sums);
-    png_scan_kernel<<<1, 1024, 0, ctx->stream>>>(block_sums, n_blocks, n_bytes, (const PngTables*)ctx->d_png_tables, ctx->d_png_off, out, info);
-    png_merge_kernel<<<n_blocks, 32 * kEncWarps, 0, ctx->stream>>>(ctx->d_png_staging, ctx->d_png_seg, ctx->d_png_off, n_seg, out);
+    png_scan_kernel<<<1, 1024, 0, stream>>>(block_sums, n_blocks, n_bytes, (const PngTables*)ctx->d_png_tables, ctx->d_png_off, out, info);
+    png_merge_kernel<<<n_blocks, 32 * kEncWarps, 0, stream>>>(ctx->d_png_staging, ctx->d_png_seg, ctx->d_png_off, n_seg, out);
     ctx->launches += 3;
     BHR_CUDA(ctx, cudaGetLastError());
     return BHR_OK;
