@@ -76,6 +76,7 @@ extern "C" int bhr_create(const bhr_config* cfg, bhr_ctx** out) {
     ctx->d_total_steps = (unsigned long long*)(ctx->d_queue_count + 4);
     ctx->retrace_min_cross = 3;
     ctx->entity_stream_on = 1;
+    ctx->entity_early = 1;
     ctx->retrace_band = 0.02f;
     ctx->band_lo_auto = 1;
     ctx->sync_bands = 1;
@@ -125,6 +126,7 @@ extern "C" void bhr_destroy(bhr_ctx* ctx) {
     if (ctx->frame_done) cudaEventDestroy(ctx->frame_done);
     if (ctx->ent_stream) { cudaStreamSynchronize(ctx->ent_stream); cudaStreamDestroy(ctx->ent_stream); }
     if (ctx->bg_start_ev) cudaEventDestroy(ctx->bg_start_ev);
+    if (ctx->comp_read_ev) cudaEventDestroy(ctx->comp_read_ev);
     if (ctx->ent_done_ev) cudaEventDestroy(ctx->ent_done_ev);
     if (ctx->h_entities) cudaFreeHost(ctx->h_entities);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -184,10 +186,11 @@ extern "C" int bhr_set_option(bhr_ctx* ctx, const char* key, double value) {
         return BHR_OK;
     }
     if (ctx && !strcmp(key, "background_blocks_per_sm")) {      // resident blocks of the packed background kernel (experiments)
-        if (value < 1) BHR_FAIL(ctx, BHR_ERR_INVALID, "background_blocks_per_sm must be >= 1");
-        ctx->bg_blocks_per_sm = (int)value;
+        if (value < 0) BHR_FAIL(ctx, BHR_ERR_INVALID, "background_blocks_per_sm must be >= 0 (0 = automatic)");
+        ctx->bg_blocks_override = (int)value;
         return BHR_OK;
     }
+    if (ctx && !strcmp(key, "entity_early")) { ctx->entity_early = value != 0.0; return BHR_OK; }
     if (ctx && !strcmp(key, "entity_stream")) {          // 1 (default): the entity layer runs on its own stream beside the background kernel
         if (int rc = bhr_join_entities(ctx)) return rc;
         ctx->entity_stream_on = value != 0.0;

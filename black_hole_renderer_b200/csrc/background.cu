@@ -283,10 +283,13 @@ int bhr_setup_background(bhr_ctx* ctx) {
 int bhr_launch_background(bhr_ctx* ctx, float t) {
     // persistent blocks (hash / gradient tables filled once each): as many as stay resident
     const int want = bhr_div_up(ctx->n_r * (ctx->n_phi / 2), 256);
-    // With the entity stream on, ONE block per SM: the two blocks that fit hold the whole register file, and the entity
-    // kernels (FP64 / XU heavy, this one FP32 heavy) are to run beside it.  Alone that costs 0.330 instead of 0.307 ms,
-    // together with the entity layer 0.391 instead of 0.435 (tools/entity_overlap.py).
-    const int cap = (ctx->entity_stream_on ? 1 : ctx->bg_blocks_per_sm) * ctx->num_sms;
+    // With the entity stream released by this kernel's start (option entity_early = 0), ONE block per SM: the two blocks
+    // that fit hold the whole register file, and the entity kernels (FP64 / XU heavy, this one FP32 heavy) are to run beside
+    // it -- alone that costs 0.330 instead of 0.307 ms, together with the entity layer 0.391 instead of 0.435
+    // (tools/entity_overlap.py).  With the early release (default) the entity layer has mostly run beside the previous
+    // frame's bloom passes by now, and two blocks are better again (video frame 1.030 vs 1.036 ms, tools/entity_stream_ab.py).
+    const int per_sm = ctx->bg_blocks_override > 0 ? ctx->bg_blocks_override : (ctx->entity_stream_on && !ctx->entity_early) ? 1 : ctx->bg_blocks_per_sm;
+    const int cap = per_sm * ctx->num_sms;
     Consts K;
     K.one = make_float2(1.0f, 1.0f); K.minus_one = make_float2(-1.0f, -1.0f); K.neg_zero = make_float2(-0.0f, -0.0f);
     background_kernel<<<want < cap ? want : cap, 256, 0, ctx->stream>>>(ctx->comp, ctx->bg_rows, ctx->n_r, ctx->n_phi, ctx->az_freq, t, K);

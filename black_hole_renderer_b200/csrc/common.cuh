@@ -98,6 +98,7 @@ struct bhr_ctx {
     int bg_ready, az_freq; float az_shear;
     float* bg_rows;                    // 3 x n_r row quantities of the background kernel (omega, decay, shear)
     int background_scalar;             // option: the one-texel-per-thread background kernel
+    int bg_blocks_override;            // option "background_blocks_per_sm" (0 = automatic)
     int bg_blocks_per_sm;              // resident blocks of the packed background kernel (background.cu)
     bhr_entity* d_entities; int entities_cap;      // 8-slot ring: entities + slot maps (texture.cu)
     float* d_entity_tables; size_t entity_tables_cap, entity_tables_n;   // tabulated profiles of caller-owned entities (kind 3 / 4)
@@ -134,6 +135,7 @@ struct bhr_ctx {
     void* d_png_tables; unsigned int* d_png_staging; unsigned int* d_png_seg; unsigned long long* d_png_off;
     uint8_t* d_png_stream[BHR_FRAME_SLOTS]; int png_n_seg; size_t png_capacity;
     // the entity layer runs on its own stream next to the background kernel (texture.cu): FP64-bound beside FP32-bound
+    cudaEvent_t comp_read_ev; int comp_read_valid, entity_early;   // "the last kernel that reads the entity planes has been enqueued"
     cudaStream_t ent_stream; cudaEvent_t bg_start_ev, ent_done_ev; int bg_start_armed, ent_pending, entity_stream_on, entity_carveout_set;
     int ev_valid;
     float tint[3];
@@ -156,6 +158,16 @@ extern char g_bhr_create_error[512];
         snprintf((ctx)->err, sizeof((ctx)->err), __VA_ARGS__);     \
         return (code);                                             \
     } while (0)
+
+// After a kernel that reads the entity planes of `comp` has been enqueued on the context's stream: the next entity layer
+// (entity stream) may start once it is done.
+static inline int bhr_mark_comp_read(bhr_ctx* ctx) {
+    if (!ctx->entity_stream_on) return BHR_OK;
+    if (!ctx->comp_read_ev) BHR_CUDA(ctx, cudaEventCreateWithFlags(&ctx->comp_read_ev, cudaEventDisableTiming));
+    BHR_CUDA(ctx, cudaEventRecord(ctx->comp_read_ev, ctx->stream));
+    ctx->comp_read_valid = 1;
+    return BHR_OK;
+}
 
 // Work on the context's stream that reads or writes the entity planes of `comp` first waits for the entity stream.
 static inline int bhr_join_entities(bhr_ctx* ctx) {

@@ -205,6 +205,7 @@ extern "C" int bhr_stats_prepare(bhr_ctx* ctx, int enable_rt, uint64_t* n_total,
     stats_prepare_kernel<<<ctx->n_r, 256, 0, ctx->stream>>>(ctx->comp, ctx->edge, ctx->n_r, ctx->n_phi,
                                                             enable_rt ? 0.20f : 0.0f, dens, strc,
                                                             row_out + 3 * (size_t)ctx->n_r, d_pos);
+    if ((rc = bhr_mark_comp_read(ctx))) return rc;
     BHR_CUDA(ctx, cudaGetLastError());
     unsigned long long pos = 0;
     BHR_CUDA(ctx, cudaMemcpyAsync(&pos, d_pos, sizeof(pos), cudaMemcpyDeviceToHost, ctx->stream));

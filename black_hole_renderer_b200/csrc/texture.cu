@@ -454,11 +454,18 @@ extern "C" int bhr_accumulate_entities(bhr_ctx* ctx, const bhr_entity* entities,
             BHR_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->ent_stream, cudaStreamNonBlocking));
             BHR_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ent_done_ev, cudaEventDisableTiming));
         }
-        if (!ctx->bg_start_ev) BHR_CUDA(ctx, cudaEventCreateWithFlags(&ctx->bg_start_ev, cudaEventDisableTiming));
-        if (!ctx->bg_start_armed) BHR_CUDA(ctx, cudaEventRecord(ctx->bg_start_ev, ctx->stream));
-        ctx->bg_start_armed = 0;
         es = ctx->ent_stream;
-        BHR_CUDA(ctx, cudaStreamWaitEvent(es, ctx->bg_start_ev, 0));
+        if (ctx->entity_early && ctx->comp_read_valid) {
+            // as early as the data allow: behind the last reader of the planes (the previous frame's compose / statistics),
+            // i.e. beside the previous frame's bloom passes as well as beside this frame's background kernel
+            BHR_CUDA(ctx, cudaStreamWaitEvent(es, ctx->comp_read_ev, 0));
+            ctx->bg_start_armed = 0;
+        } else {
+            if (!ctx->bg_start_ev) BHR_CUDA(ctx, cudaEventCreateWithFlags(&ctx->bg_start_ev, cudaEventDisableTiming));
+            if (!ctx->bg_start_armed) BHR_CUDA(ctx, cudaEventRecord(ctx->bg_start_ev, ctx->stream));
+            ctx->bg_start_armed = 0;
+            BHR_CUDA(ctx, cudaStreamWaitEvent(es, ctx->bg_start_ev, 0));
+        }
     }
     if (n > ctx->entities_cap) {
         BHR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -584,6 +591,7 @@ extern "C" int bhr_compose_texture(bhr_ctx* ctx, float t_offset, int enable_rt, 
         ctx->comp, ctx->omega_rows, ctx->edge, ctx->stats[0], ctx->stats[1], ctx->row_stats, ctx->n_r, ctx->n_phi,
         t_offset, enable_rt, color_temp, ctx->mips);
     ++ctx->launches;
+    if (int rc = bhr_mark_comp_read(ctx)) return rc;
     BHR_CUDA(ctx, cudaGetLastError());
     return bhr_launch_build_mips(ctx, 0);
 }

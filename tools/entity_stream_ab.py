@@ -13,9 +13,10 @@ r = Renderer(W, H, synthetic_skybox(), np.zeros((n_r, n_phi, 4), np.float32))
 r.set_option("stage_timing", 0)
 frames = {}
 for rep in range(2):
-    for es, blocks in ((0, 2), (1, 2), (1, 1), (0, 1)):
+    for es, early, blocks in ((0, 0, 2), (1, 0, 1), (1, 1, 1), (1, 1, 2), (1, 0, 2)):
         F = init_lifecycle_system(r, n_r, n_phi, seed=42)
         r.set_option("entity_stream", es)
+        r.set_option("entity_early", early)
         r.set_option("background_blocks_per_sm", blocks)
         r.synchronize()
         keep = {}
@@ -25,4 +26,4 @@ for rep in range(2):
         r.synchronize()
         ms = (time.perf_counter() - t0) / 600 * 1e3
         same = all(np.array_equal(keep[f], frames.setdefault(f, keep[f])) for f in keep)
-        print(f"entity_stream {es} bg blocks/SM {blocks}: {ms:.4f} ms/frame, frames identical to the first run: {same}", flush=True)
+        print(f"entity_stream {es} early {early} bg blocks/SM {blocks}: {ms:.4f} ms/frame, frames identical to the first run: {same}", flush=True)
