@@ -194,7 +194,7 @@ extern "C" int bhr_set_option(bhr_ctx* ctx, const char* key, double value) {
     if (ctx && !strcmp(key, "entity_stream")) {          // 1 (default): the entity layer runs on its own stream beside the background kernel
         if (int rc = bhr_join_entities(ctx)) return rc;
         ctx->entity_stream_on = value != 0.0;
-        return BHR_OK;
+        return bhr_mark_comp_read(ctx);          // (turned on: the next entity layer starts behind everything enqueued so far)
     }
     if (ctx && !strcmp(key, "background_scalar")) { ctx->background_scalar = (int)value; return BHR_OK; }
     if (ctx) snprintf(ctx->err, sizeof(ctx->err), "unknown option %s", key);

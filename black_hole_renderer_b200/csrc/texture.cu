@@ -399,7 +399,9 @@ extern "C" int bhr_init_background(bhr_ctx* ctx, int n_r, int n_phi, int az_freq
         BHR_CUDA(ctx, cudaMalloc(&ctx->omega_rows, n_r * sizeof(float)));
         BHR_CUDA(ctx, cudaMalloc(&ctx->row_stats, 2 * n_r * sizeof(float)));
     }
+    if ((rc = bhr_join_entities(ctx))) return rc;            // (an entity layer still in flight on its own stream)
     BHR_CUDA(ctx, cudaMemsetAsync(ctx->comp, 0, plane * BHR_N_COMP * sizeof(float), ctx->stream));
+    if ((rc = bhr_mark_comp_read(ctx))) return rc;           // (... and the next one starts behind this clear)
     BHR_CUDA(ctx, cudaMemcpyAsync(ctx->edge, edge, n_r * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     BHR_CUDA(ctx, cudaMemcpyAsync(ctx->omega_rows, omega_rows, n_r * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     BHR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -577,6 +579,7 @@ extern "C" int bhr_upload_comp(bhr_ctx* ctx, const float* comp) {
     const size_t bytes = (size_t)ctx->n_r * ctx->n_phi * BHR_N_COMP * sizeof(float);
     if (int rc = bhr_join_entities(ctx)) return rc;
     BHR_CUDA(ctx, cudaMemcpyAsync(ctx->comp, comp, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (int rc = bhr_mark_comp_read(ctx)) return rc;
     BHR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return BHR_OK;
 }

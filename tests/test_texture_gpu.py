@@ -344,3 +344,25 @@ def test_pipeline_stage_time_budgets():
     assert ms["background"] < 5.0 and ms["entities"] < 2.0 and ms["compose"] < 0.5 and ms["stats"] < 2.0, ms
     assert sum(ms.values()) < 8.0, ms
     assert np.isfinite(r.disk_texture_field.to_numpy()).all() and r.disk_texture_field.to_numpy()[..., :3].max() > 0.05
+
+
+def test_entity_stream_orders_the_planes_like_one_stream():
+    """The entity layer runs on its own stream beside the background kernel (options entity_stream / entity_early): the
+    component planes, the statistics and the composed texture of a run of video frames must not depend on it -- back to
+    back frames without any host synchronisation in between, which is where a missing event would show."""
+    from black_hole_renderer_b200 import lifecycle as LC
+    n_r, n_phi = 96, 640
+    outs = {}
+    for mode in ((0, 0), (1, 0), (1, 1)):
+        r = _renderer(n_r, n_phi)
+        r.set_option("entity_stream", mode[0])
+        r.set_option("entity_early", mode[1])
+        F = LC.init_lifecycle_system(r, n_r, n_phi, seed=7)
+        for frame in range(1, 70):                     # crosses a statistics block boundary (frame 60)
+            LC.advance_lifecycle_frame(r, F, t=0.1 * frame, dt=0.1, recompute_stats=(frame % 60 == 0))
+            r.render_device([6, 0, 0.5], 90)
+        outs[mode] = (r._comp_field.to_numpy(), r.disk_texture_field.to_numpy(), r._param_stats_field.to_numpy())
+        r.close()
+    for mode in ((1, 0), (1, 1)):
+        for a, b in zip(outs[(0, 0)], outs[mode]):
+            assert np.array_equal(a, b), mode
