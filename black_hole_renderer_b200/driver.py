@@ -18,7 +18,7 @@ import numpy as np
 from PIL import Image
 
 from .lifecycle import advance_lifecycle_frame, init_lifecycle_system
-from .png_codec import png_container
+from .png_codec import png_container, png_container_parts
 from .renderer import R_DISK_INNER_DEFAULT, R_DISK_OUTER_DEFAULT, Renderer, compute_edge_alpha
 from .skybox import load_or_generate_skybox
 
@@ -332,9 +332,15 @@ def render_video(renderer, width, height, n_frames, fps, output_path, fov, stati
     if hasattr(renderer, "set_option"):
         renderer.set_option("stage_timing", 0)      # no per-stage timing events in the frame loop
 
-    # PNG encoding is host work outside the render path and the wall-clock limit of a video run
-    # (tens of ms per 1080p frame and core): use the host's cores for it
-    pool = ThreadPoolExecutor(max_workers=int(os.environ.get("BHR_PNG_WORKERS", str(min(16, os.cpu_count() or 2)))))
+    # the deflate stream comes from the device (csrc/png.cu) unless BHR_PNG_DEVICE=0: the host then only frames it
+    # (chunk lengths, CRC-32) and writes the file
+    device_png = os.environ.get("BHR_PNG_DEVICE", "1") != "0" and hasattr(renderer, "render_png_async")
+
+    # File writers.  With the streams from the device a writer only frames and writes (CRC-32 and write() release the GIL):
+    # two to four threads keep up and more only contend with the frame loop for the GIL (measured 862 / 824 / 805 / 837
+    # frames/s with 2 / 4 / 8 / 16).  The host-side encoder (tens of ms of zlib per 1080p frame and core) uses the cores.
+    default_workers = min(3, os.cpu_count() or 2) if device_png else min(16, os.cpu_count() or 2)
+    pool = ThreadPoolExecutor(max_workers=int(os.environ.get("BHR_PNG_WORKERS", str(default_workers))))
     png_level = int(os.environ.get("BHR_PNG_LEVEL", "1"))
     jobs = {}                                  # frame -> future of its PNG file
     mine_done = set()                          # frames of THIS run whose file is on disk
@@ -345,14 +351,11 @@ def render_video(renderer, width, height, n_frames, fps, output_path, fov, stati
             f.write(encode_png(img_u8, png_level))
         os.replace(tmp, path)                  # a crash never leaves a truncated frame under the final name
 
-    # the deflate stream comes from the device (csrc/png.cu) unless BHR_PNG_DEVICE=0: the host then only frames it
-    # (chunk lengths, CRC-32) and writes the file
-    device_png = os.environ.get("BHR_PNG_DEVICE", "1") != "0" and hasattr(renderer, "render_png_async")
-
     def save_stream(path, stream):
         tmp = path + ".part"
         with open(tmp, "wb") as f:
-            f.write(png_container(width, height, stream))
+            for part in png_container_parts(width, height, stream):     # (no copy of the stream: CRC-32 and write release the GIL)
+                f.write(part)
         os.replace(tmp, path)
 
     def sink(frame, data):

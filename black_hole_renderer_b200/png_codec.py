@@ -258,12 +258,23 @@ def encode_stream_reference(filtered):
     return w.bytes_padded() + struct.pack(">I", zlib.adler32(filtered.tobytes())), seg_bits
 
 
-def png_container(width, height, zlib_stream):
-    """PNG file bytes around a finished zlib stream (8-bit RGB, no interlace)."""
+def png_container_parts(width, height, zlib_stream):
+    """The PNG file around a finished zlib stream (8-bit RGB, no interlace) as (head, stream, tail): write the three
+    in order.  The stream (any buffer: a view of a pinned ring buffer in the video loop) is not copied; its CRC-32
+    and the write release the GIL."""
     def chunk(tag, payload):
         return struct.pack(">I", len(payload)) + tag + payload + struct.pack(">I", zlib.crc32(payload, zlib.crc32(tag)))
-    return (b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", width, height, 8, 2, 0, 0, 0))
-            + chunk(b"IDAT", bytes(zlib_stream)) + chunk(b"IEND", b""))
+    view = memoryview(zlib_stream).cast("B")
+    head = (b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", width, height, 8, 2, 0, 0, 0))
+            + struct.pack(">I", view.nbytes) + b"IDAT")
+    tail = struct.pack(">I", zlib.crc32(view, zlib.crc32(b"IDAT"))) + chunk(b"IEND", b"")
+    return head, view, tail
+
+
+def png_container(width, height, zlib_stream):
+    """PNG file bytes around a finished zlib stream."""
+    head, view, tail = png_container_parts(width, height, zlib_stream)
+    return head + bytes(view) + tail
 
 
 def encode_frame_reference(img_u8):
