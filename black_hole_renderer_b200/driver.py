@@ -11,6 +11,7 @@ import json
 import math
 import os
 import shutil
+import struct
 import time
 from concurrent.futures import ThreadPoolExecutor
 
@@ -18,6 +19,7 @@ import numpy as np
 from PIL import Image
 
 from .lifecycle import advance_lifecycle_frame, init_lifecycle_system
+from .mov import write_png_movie
 from .png_codec import png_container, png_container_parts
 from .renderer import R_DISK_INNER_DEFAULT, R_DISK_OUTER_DEFAULT, Renderer, compute_edge_alpha
 from .skybox import load_or_generate_skybox
@@ -403,22 +405,37 @@ def render_video(renderer, width, height, n_frames, fps, output_path, fov, stati
     if len(completed) < n_frames:
         print(f"Warning: only {len(completed)}/{n_frames} frames completed. Run again to resume.")
         return
-    mux_video(temp_dir, n_frames, fps, output_path)
+    mux_video(temp_dir, n_frames, fps, output_path, width, height)
 
 
-def mux_video(temp_dir, n_frames, fps, output_path):
-    """x264 mux through imageio/pyav as the reference does (render.py:4497-4503); host I/O,
-    outside the render path -- skipped with a hint when imageio is not installed."""
-    try:
-        import imageio.v3 as iio
-    except Exception:
-        print(f"imageio not available: frames kept in {temp_dir}; encode with\n"
-              f"  ffmpeg -framerate {fps} -i {temp_dir}/frame_%04d.png -c:v libx264 -crf 18 "
-              f"-pix_fmt yuv420p {output_path}")
-        return
-    writer = iio.imopen(output_path, "w", plugin="pyav")
-    writer.init_video_stream("libx264", fps=fps)
-    for frame in range(n_frames):
-        writer.write_frame(iio.imread(os.path.join(temp_dir, f"frame_{frame:04d}.png")))
-    writer.close()
+def mux_video(temp_dir, n_frames, fps, output_path, width=None, height=None):
+    """Frame files -> video file (render.py:4497-4503).  The reference re-encodes the PNGs with x264
+    through imageio / pyav; that path is taken when imageio is installed (or BHR_MUX=x264 asks for
+    it).  Otherwise -- and this image has neither imageio nor an H.264 encoder -- the frame files,
+    whose deflate streams the GPU already produced, become the samples of a QuickTime 'png ' movie
+    (mov.write_png_movie): a lossless file copy, no second encoder, readable by ffmpeg / OpenCV."""
+    mode = os.environ.get("BHR_MUX", "auto")
+    files = [os.path.join(temp_dir, f"frame_{frame:04d}.png") for frame in range(n_frames)]
+    iio = None
+    if mode in ("auto", "x264"):
+        try:
+            import imageio.v3 as iio
+        except Exception:
+            if mode == "x264":
+                raise
+    if iio is not None:
+        writer = iio.imopen(output_path, "w", plugin="pyav")
+        writer.init_video_stream("libx264", fps=fps)
+        for path in files:
+            writer.write_frame(iio.imread(path))
+        writer.close()
+    else:
+        if width is None or height is None:
+            with open(files[0], "rb") as f:
+                width, height = struct.unpack(">II", f.read(24)[16:24])       # IHDR
+        t0 = time.time()
+        write_png_movie(output_path, files, width, height, fps)
+        print(f"Muxed {n_frames} PNG frames into a QuickTime 'png ' movie in {time.time() - t0:.2f} s "
+              f"({os.path.getsize(output_path) / 1e6:.1f} MB, lossless; x264 instead: install imageio + av, or\n"
+              f"  ffmpeg -i {output_path} -c:v libx264 -crf 18 -pix_fmt yuv420p out.mp4)")
     print(f"Video saved: {output_path}")

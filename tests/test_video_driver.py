@@ -215,3 +215,55 @@ def test_device_png_streams_become_the_frame_files(tmp_path):
         assert (getattr(r, "fetches", 0) > 0) == starve
         # after the first frames retire, the copy size follows the streams instead of the buffer size
         assert starve or r.copies[-1] <= r.copies[0]
+
+
+def test_video_file_is_a_lossless_movie_of_the_frame_files(tmp_path):
+    """Without imageio the frame files become the samples of a QuickTime 'png ' movie (mov.py): the
+    index lists every frame file byte for byte, and a stock demuxer + PNG decoder (OpenCV's ffmpeg)
+    reads back exactly the rendered frames at the requested rate."""
+    from black_hole_renderer_b200 import mov
+    os.environ["BHR_MUX"] = "png"
+    try:
+        d = _run(tmp_path, FakeRenderer(), n_frames=12, degrees=90.0)
+    finally:
+        del os.environ["BHR_MUX"]
+    out = tmp_path / "v.mp4"
+    assert out.exists() and not os.path.exists(str(out) + ".part")
+    w, h, fps, index = mov.read_png_movie_index(out)
+    assert (w, h, fps, len(index)) == (8, 4, 4.0, 12)
+    blob = open(out, "rb").read()
+    for f, (off, size) in enumerate(index):
+        assert blob[off:off + size] == open(d / f"frame_{f:04d}.png", "rb").read()
+    try:
+        import cv2
+    except Exception:
+        return
+    cap = cv2.VideoCapture(str(out))
+    assert cap.isOpened() and cap.get(cv2.CAP_PROP_FPS) == 4.0 and int(cap.get(cv2.CAP_PROP_FRAME_COUNT)) == 12
+    for f in range(12):
+        ok, bgr = cap.read()
+        assert ok and bgr.shape == (4, 8, 3) and np.all(bgr == (f + 1) % 251)
+    assert not cap.read()[0]
+
+
+def test_png_movie_accepts_streams_and_rejects_garbage(tmp_path):
+    from black_hole_renderer_b200 import mov, png_codec
+    import pytest
+    rng = np.random.default_rng(3)
+    frames = [rng.integers(0, 256, (9, 16, 3), dtype=np.uint8) for _ in range(3)]
+    streams = [png_codec.encode_stream_reference(png_codec.sub_filter(f))[0] for f in frames]
+    parts = [png_codec.png_container_parts(16, 9, s) for s in streams]        # (head, stream view, tail) as the video loop writes them
+    whole = [png_codec.png_container(16, 9, s) for s in streams]
+    assert whole[0] == png_codec.encode_frame_reference(frames[0])
+    assert mov.write_png_movie(str(tmp_path / "a.mov"), parts, 16, 9, 29.97) == 3
+    assert mov.write_png_movie(str(tmp_path / "b.mov"), whole, 16, 9, 29.97) == 3
+    assert open(tmp_path / "a.mov", "rb").read() == open(tmp_path / "b.mov", "rb").read()
+    w, h, fps, index = mov.read_png_movie_index(tmp_path / "a.mov")
+    assert (w, h, len(index)) == (16, 9, 3) and abs(fps - 29.97) < 1e-9
+    bad = tmp_path / "bad.png"
+    bad.write_bytes(b"not a png")
+    with pytest.raises(ValueError):
+        mov.write_png_movie(str(tmp_path / "c.mov"), [str(bad)], 16, 9, 30)
+    with pytest.raises(ValueError):
+        mov.write_png_movie(str(tmp_path / "d.mov"), [], 16, 9, 30)
+    assert not (tmp_path / "c.mov").exists() and not (tmp_path / "d.mov").exists()
