@@ -124,3 +124,43 @@ def test_frame_sharding_blocks_of_60():
     cam = orbit_camera([6, 0, 0.5], 900, 3600, 360.0)
     assert abs(np.hypot(cam[0], cam[1]) - np.sqrt(36.25)) < 1e-12 and cam[2] == 0.5
     assert abs(cam[0]) < 1e-9 and cam[1] > 0
+
+
+def _video_worker(rank, world, port, out_dir):
+    """One rank of a sharded `render.py --video` run with a fake renderer: the control plane (gloo
+    barriers, per-rank progress files, rank 0 merging and muxing) is the real one (render.py:91-103)."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["BHR_MUX"] = "png"
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from test_video_driver import FakeRenderer
+    from black_hole_renderer_b200.driver import render_video
+    r = FakeRenderer()
+    render_video(r, 8, 4, n_frames=150, fps=30, output_path=os.path.join(out_dir, "v.mp4"), fov=90.0,
+                 static_cam_pos=[6, 0, 0.5], orbit=True, resume=False, disk_rotation_speed=0.1,
+                 orbit_degrees=360.0, rank=rank, world_size=world, barrier=dist.barrier)
+    np.save(os.path.join(out_dir, f"cams{rank}.npy"), np.array(r.cams))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_video_run_over_gloo_ranks(tmp_path):
+    """Two processes share one 150-frame job in 60-frame blocks (rank 0: frames 0-59 and 120-149,
+    rank 1: 60-119), no data-path collective; rank 0 merges the progress lists and writes the movie
+    with every frame in order."""
+    import json
+    from black_hole_renderer_b200 import mov
+    mp.spawn(_video_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    frames_dir = [d for d in os.listdir(tmp_path) if d.startswith(".frames_")][0]
+    d = tmp_path / frames_dir
+    assert sorted(json.load(open(d / "progress.json"))["completed"]) == list(range(150))
+    assert len(np.load(tmp_path / "cams0.npy")) == 90 and len(np.load(tmp_path / "cams1.npy")) == 60
+    # rank 1's first camera is the orbit position of frame 60
+    a = np.radians(60 * 360.0 / 150)
+    np.testing.assert_allclose(np.load(tmp_path / "cams1.npy")[0], [np.sqrt(36.25) * np.cos(a), np.sqrt(36.25) * np.sin(a), 0.5], atol=1e-12)
+    w, h, fps, index = mov.read_png_movie_index(tmp_path / "v.mp4")
+    assert (w, h, fps, len(index)) == (8, 4, 30.0, 150)
+    blob = open(tmp_path / "v.mp4", "rb").read()
+    for f in (0, 59, 60, 119, 120, 149):
+        off, size = index[f]
+        assert blob[off:off + size] == open(d / f"frame_{f:04d}.png", "rb").read()
