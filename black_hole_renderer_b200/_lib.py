@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbhr.so")
+LIB_PATH = os.environ.get("BHR_LIB") or os.path.join(_HERE, "libbhr.so")      # (BHR_LIB: A/B of two builds, tools/lib_ab.py)
 
 BHR_SKIP_DIFFERENTIALS = 1
 BHR_SKIP_BLOOM = 2
