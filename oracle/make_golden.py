@@ -75,6 +75,14 @@ RAY_CASES = {
     "raymarch_offaxis_fine": dict(w=20, h=12, pov=[4, 3, 2], fov=75, step=0.05, r_max=30.0,
                                   r_in=1.5, r_out=9.0, tilt=-35.0, flare=True, aa="lod_radius",
                                   aa_strength=1.5, dtex=(32, 128)),
+    # render(frame != 0): the samplers rotate the texture by t_offset * Omega(r), t_offset = frame * disk_rotation_speed
+    # (render.py:3897, 2569-2575, 2601-2607); no live caller of the reference does this, the API does
+    "raymarch_frame_rot": dict(w=36, h=20, pov=[6, 0, 0.5], fov=90, step=0.1, r_max=10.0,
+                               r_in=2.0, r_out=15.0, tilt=0.0, flare=False, aa="disabled",
+                               aa_strength=1.0, dtex=(32, 128), frame=12, speed=0.25),
+    "raymarch_frame_rot_aa": dict(w=32, h=18, pov=[5, -2, 1.5], fov=80, step=0.1, r_max=10.0,
+                                  r_in=2.0, r_out=12.0, tilt=10.0, flare=False, aa="lod_radius",
+                                  aa_strength=1.0, dtex=(64, 256), frame=37, speed=0.1),
 }
 
 
@@ -84,14 +92,15 @@ def gen_raymarch(name, c):
     r = ref.TaichiRenderer(c["w"], c["h"], skybox, disk, step_size=c["step"], r_max=c["r_max"],
                            device="cpu", r_disk_inner=c["r_in"], r_disk_outer=c["r_out"],
                            disk_tilt=c["tilt"], lens_flare=c["flare"], anti_alias=c["aa"],
-                           aa_strength=c["aa_strength"])
+                           aa_strength=c["aa_strength"], disk_rotation_speed=c.get("speed", 0.1))
+    frame = c.get("frame", 0)
     t0 = time.time()
-    final = r.render(c["pov"], c["fov"], frame=0)
+    final = r.render(c["pov"], c["fov"], frame=frame)
     out = dict(
         skybox=skybox.astype(np.float32), disk_tex=disk,
         params=np.array([c["w"], c["h"], *c["pov"], c["fov"], c["step"], c["r_max"], c["r_in"],
                          c["r_out"], c["tilt"], float(c["flare"]),
-                         float(c["aa"] != "disabled"), c["aa_strength"]], dtype=np.float64),
+                         float(c["aa"] != "disabled"), c["aa_strength"], frame, c.get("speed", 0.1)], dtype=np.float64),
         # reference fields are (W, H, 3); stored transposed to (H, W, 3) like render()'s return
         bg=r.image_field.to_numpy().transpose(1, 0, 2),
         # NB: read after render(), i.e. after _bloom_kernel's in-place `+= 0.4*blur`
@@ -103,13 +112,13 @@ def gen_raymarch(name, c):
     )
     # skip_bloom / skip_differentials variants of the same call (render.py:3911-3912, 3900)
     out["final_skip_bloom"] = np.asarray(
-        r.render(c["pov"], c["fov"], frame=0, skip_bloom=True), dtype=np.float32)
+        r.render(c["pov"], c["fov"], frame=frame, skip_bloom=True), dtype=np.float32)
     out["disk_layer"] = r.disk_layer_field.to_numpy().transpose(1, 0, 2)   # pre-bloom
     if c["aa"] != "disabled":
         lf = r.lens_flare
         r.lens_flare = False
         out["final_skip_diff"] = np.asarray(
-            r.render(c["pov"], c["fov"], frame=0, skip_differentials=True, skip_bloom=True),
+            r.render(c["pov"], c["fov"], frame=frame, skip_differentials=True, skip_bloom=True),
             dtype=np.float32)
         r.lens_flare = lf
     print(f"  {name}: {time.time() - t0:.1f}s  final mean={final.mean():.5f}")

@@ -10,7 +10,8 @@ import pytest
 import oracle as O
 from util import GOLDEN
 
-CASES = ["raymarch_default", "raymarch_aa_tilt_flare", "raymarch_e2e_like", "raymarch_offaxis_fine"]
+CASES = ["raymarch_default", "raymarch_aa_tilt_flare", "raymarch_e2e_like", "raymarch_offaxis_fine",
+         "raymarch_frame_rot", "raymarch_frame_rot_aa"]      # the last two: render(frame != 0), rotated texture lookups
 TOL = 2e-6
 
 
@@ -19,6 +20,8 @@ def _render_case(d, **over):
     kw = dict(step_size=p[6], r_max=p[7], r_inner=p[8], r_outer=p[9], disk_tilt=p[10],
               anti_alias="lod_radius" if p[12] else "disabled", aa_strength=p[13])
     flare = bool(p[11])
+    if len(p) > 14:                       # t_offset = float(frame) * disk_rotation_speed (render.py:3897)
+        kw["t_offset"] = float(p[14]) * float(p[15])
     kw.update(over)
     flare = kw.pop("lens_flare_on", flare)
     return O.render(int(p[0]), int(p[1]), p[2:5], p[5], d["skybox"], d["disk_tex"], mips=d["mips"],

@@ -18,7 +18,8 @@ from util import GOLDEN, RESOLUTIONS, parity_report, synthetic_disk_texture, syn
 
 pytestmark = pytest.mark.gpu
 
-CASES = ["raymarch_default", "raymarch_aa_tilt_flare", "raymarch_e2e_like", "raymarch_offaxis_fine"]
+CASES = ["raymarch_default", "raymarch_aa_tilt_flare", "raymarch_e2e_like", "raymarch_offaxis_fine",
+         "raymarch_frame_rot", "raymarch_frame_rot_aa"]      # the last two: render(frame != 0), rotated texture lookups
 MODES = {"fast": 0, "strict": 2}
 
 
@@ -27,9 +28,10 @@ def _renderer_for(d, mode):
     p = d["params"]
     r = Renderer(int(p[0]), int(p[1]), d["skybox"], d["disk_tex"], step_size=p[6], r_max=p[7],
                  r_disk_inner=p[8], r_disk_outer=p[9], disk_tilt=p[10], lens_flare=bool(p[11]),
-                 anti_alias="lod_radius" if p[12] else "disabled", aa_strength=p[13])
+                 anti_alias="lod_radius" if p[12] else "disabled", aa_strength=p[13],
+                 disk_rotation_speed=p[15] if len(p) > 14 else 0.1)
     r.set_option("raymarch_mode", MODES[mode])
-    return r, list(p[2:5]), p[5]
+    return r, list(p[2:5]), p[5], (int(p[14]) if len(p) > 14 else 0)
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -37,18 +39,18 @@ def test_strict_mode_matches_reference_goldens(name):
     """Reference operation order, exactly rounded: equal to the reference's own output up to the
     few-ulp differences of the device libm in the shading / sampling code."""
     d = np.load(os.path.join(GOLDEN, name + ".npz"))
-    r, pov, fov = _renderer_for(d, "strict")
-    img = r.render(pov, fov)
+    r, pov, fov, frame = _renderer_for(d, "strict")
+    img = r.render(pov, fov, frame=frame)
     assert np.abs(img - d["final"]).max() < 2e-5
     assert np.abs(r.image_field.to_numpy().transpose(1, 0, 2) - d["bg"]).max() < 2e-5
     # (after a bloomed frame the field holds clamp(layer + 0.4 blur), render.py:3112-3114)
     assert np.abs(r.disk_layer_field.to_numpy().transpose(1, 0, 2) - d["disk_layer_after_bloom"]).max() < 2e-5
     assert np.abs(r.blur_field.to_numpy().transpose(1, 0, 2) - d["blur"]).max() < 2e-5
-    assert np.abs(r.render(pov, fov, skip_bloom=True) - d["final_skip_bloom"]).max() < 2e-5
+    assert np.abs(r.render(pov, fov, frame=frame, skip_bloom=True) - d["final_skip_bloom"]).max() < 2e-5
     assert np.abs(r.disk_layer_field.to_numpy().transpose(1, 0, 2) - d["disk_layer"]).max() < 2e-5
     if "final_skip_diff" in d.files:
         r.lens_flare = False
-        img = r.render(pov, fov, skip_differentials=True, skip_bloom=True)
+        img = r.render(pov, fov, frame=frame, skip_differentials=True, skip_bloom=True)
         assert np.abs(img - d["final_skip_diff"]).max() < 2e-5
 
 
@@ -56,8 +58,8 @@ def test_strict_mode_matches_reference_goldens(name):
 @pytest.mark.parametrize("name", CASES)
 def test_fast_modes_match_reference_goldens(name, mode):
     d = np.load(os.path.join(GOLDEN, name + ".npz"))
-    r, pov, fov = _renderer_for(d, mode)
-    img = r.render(pov, fov)
+    r, pov, fov, frame = _renderer_for(d, mode)
+    img = r.render(pov, fov, frame=frame)
     rep = parity_report(img, d["final"])
     # tiny frames: a single boundary pixel is > 0.01 %, so allow <= 1 pixel beyond 2/255
     assert rep["n_gt2"] <= 1 and rep["psnr"] >= 45.0, rep
@@ -448,7 +450,7 @@ def test_render_to_field_matches_reference_golden(name):
     the disk layer field is left post-bloom, after render() as well (render.py:3112-3114)."""
     d = np.load(os.path.join(GOLDEN, name + ".npz"))
     g = np.load(os.path.join(GOLDEN, "render_to_field.npz"))
-    r, pov, fov = _renderer_for(d, "strict")                   # (lens_flare on in the second case)
+    r, pov, fov, _ = _renderer_for(d, "strict")                   # (lens_flare on in the second case)
     W, H = r.width, r.height
     r.render_to_field(pov, fov)
     got = r.final_field.to_numpy()
