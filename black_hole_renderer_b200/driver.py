@@ -413,9 +413,23 @@ def mux_video(temp_dir, n_frames, fps, output_path, width=None, height=None):
     through imageio / pyav; that path is taken when imageio is installed (or BHR_MUX=x264 asks for
     it).  Otherwise -- and this image has neither imageio nor an H.264 encoder -- the frame files,
     whose deflate streams the GPU already produced, become the samples of a QuickTime 'png ' movie
-    (mov.write_png_movie): a lossless file copy, no second encoder, readable by ffmpeg / OpenCV."""
+    (mov.write_png_movie): a lossless file copy, no second encoder, readable by ffmpeg / OpenCV.
+    BHR_MUX=mp4v re-encodes the frames with OpenCV's MPEG-4 encoder instead (small file, lossy, slow)."""
     mode = os.environ.get("BHR_MUX", "auto")
     files = [os.path.join(temp_dir, f"frame_{frame:04d}.png") for frame in range(n_frames)]
+    if mode == "mp4v":
+        # a compact lossy file without imageio: OpenCV's bundled ffmpeg has no H.264 encoder, MPEG-4 part 2 it has
+        # (single-threaded, ~50 1080p frames/s: an option, not the default)
+        import cv2
+        first = cv2.imread(files[0], cv2.IMREAD_COLOR)
+        writer = cv2.VideoWriter(output_path, cv2.VideoWriter_fourcc(*"mp4v"), float(fps), (first.shape[1], first.shape[0]))
+        if not writer.isOpened():
+            raise RuntimeError("OpenCV cannot open an mp4v writer for " + output_path)
+        for path in files:
+            writer.write(cv2.imread(path, cv2.IMREAD_COLOR))
+        writer.release()
+        print(f"Video saved: {output_path}")
+        return
     iio = None
     if mode in ("auto", "x264"):
         try:

@@ -267,3 +267,27 @@ def test_png_movie_accepts_streams_and_rejects_garbage(tmp_path):
     with pytest.raises(ValueError):
         mov.write_png_movie(str(tmp_path / "d.mov"), [], 16, 9, 30)
     assert not (tmp_path / "c.mov").exists() and not (tmp_path / "d.mov").exists()
+
+
+def test_mp4v_mux_option(tmp_path):
+    """BHR_MUX=mp4v: a compact lossy file through OpenCV (when it is installed)."""
+    import pytest
+    cv2 = pytest.importorskip("cv2")
+    from black_hole_renderer_b200.driver import encode_png, mux_video
+    frames = []
+    for f in range(6):
+        img = np.zeros((48, 64, 3), np.uint8)
+        img[8:40, 4 + 6 * f:30 + 6 * f] = (200, 120, 40)
+        frames.append(img)
+        with open(tmp_path / f"frame_{f:04d}.png", "wb") as fh:
+            fh.write(encode_png(img))
+    os.environ["BHR_MUX"] = "mp4v"
+    try:
+        mux_video(str(tmp_path), 6, 12, str(tmp_path / "v.mp4"))
+    finally:
+        del os.environ["BHR_MUX"]
+    cap = cv2.VideoCapture(str(tmp_path / "v.mp4"))
+    assert cap.isOpened() and int(cap.get(cv2.CAP_PROP_FRAME_COUNT)) == 6
+    for f in range(6):
+        ok, bgr = cap.read()
+        assert ok and np.abs(bgr[..., ::-1].astype(int) - frames[f].astype(int)).mean() < 6.0
