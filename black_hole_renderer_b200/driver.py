@@ -10,7 +10,6 @@ import hashlib
 import json
 import math
 import os
-import shutil
 import struct
 import time
 from concurrent.futures import ThreadPoolExecutor
@@ -20,7 +19,7 @@ from PIL import Image
 
 from .lifecycle import advance_lifecycle_frame, init_lifecycle_system
 from .mov import write_png_movie
-from .png_codec import png_container, png_container_parts
+from .png_codec import png_container_parts
 from .renderer import R_DISK_INNER_DEFAULT, R_DISK_OUTER_DEFAULT, Renderer, compute_edge_alpha
 from .skybox import load_or_generate_skybox
 

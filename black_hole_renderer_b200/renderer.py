@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 from . import _lib as L
-from .camera import build_camera, build_camera_scalar
+from .camera import build_camera_scalar
 
 R_DISK_INNER_DEFAULT = 2.0
 R_DISK_OUTER_DEFAULT = 15.0
